@@ -1,0 +1,228 @@
+/*
+ * rt_b200.h — C ABI of the B200-native path-tracing hot path.
+ *
+ * This is the drop-in boundary for ONE path of df07/mcp-raytracer: the per-pixel
+ * path tracer behind `Camera.render` / `Camera.renderRegion`
+ * (reference: src/camera.ts:388-446) and everything it calls.  The reference has no
+ * FFI of its own; the seam is the TypeScript method pair the orchestration layer calls
+ * (src/raytracer.ts:59 serial, src/render-utils/renderWorker.ts:26 per worker).  What
+ * crosses that seam in the reference is plain JSON `SceneData` + `RenderOptions`
+ * (src/render-utils/renderWorker.ts:8-14), so that is what this ABI carries — flattened
+ * into SoA arrays by the host language (TypeScript in the reference; Python here, see
+ * mcp_raytracer_b200/scene_data.py and INTEGRATION.md for the N-API binding).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types, no exceptions across the ABI.
+ *   - every function returns an rt_status; rt_last_error() gives a thread-local message.
+ *   - the caller owns every host buffer for the duration of the call; the library owns
+ *     device memory behind the opaque rt_camera handle.
+ *   - scalars the reference keeps as JS numbers (radius, fuzz, ior, weight, vfov, aperture,
+ *     focus, aspect, aTolerance) travel as double; vectors the reference stores in gl-matrix
+ *     Float32Array (src/geometry/vec3.ts:21) also travel as double and are rounded to FP32
+ *     by the consumer exactly where `Vec3.create` would round them (src/geometry/vec3.ts:263).
+ *
+ * The same rt_scene_desc / rt_render_opts structs are consumed by the CPU oracle under
+ * oracle/ (test infrastructure only) so that both sides see bit-identical inputs.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef enum rt_status {
+  RT_OK = 0,
+  RT_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad size, bad region */
+  RT_ERR_UNKNOWN_OBJECT_TYPE = 2, /* reference: `Unknown object type` src/scenes/scenes.ts:137 */
+  RT_ERR_UNKNOWN_MATERIAL_TYPE = 3, /* reference: `Unknown material type` src/scenes/scenes.ts:178 */
+  RT_ERR_MATERIAL_NOT_FOUND = 4, /* reference: `Material not found` src/scenes/scenes.ts:154,191 */
+  RT_ERR_NOT_DIELECTRIC = 5, /* reference: `Material is not a dielectric` src/scenes/scenes.ts:195 */
+  RT_ERR_BUFFER_TOO_SMALL = 6, /* reference: empty pixelData src/raytracer.ts:97-99 */
+  RT_ERR_NO_DEVICE = 7, /* no CUDA device: there is NO CPU fallback */
+  RT_ERR_CUDA = 8, /* a CUDA runtime call failed; message in rt_last_error() */
+  RT_ERR_UNSUPPORTED = 9
+} rt_status;
+
+/* SceneObject.type — src/scenes/sceneData.ts:40-70 */
+enum { RT_OBJ_SPHERE = 0, RT_OBJ_PLANE = 1, RT_OBJ_QUAD = 2 };
+
+/* MaterialData.type — src/scenes/sceneData.ts:76-110 */
+enum {
+  RT_MAT_LAMBERT = 0, /* color = albedo */
+  RT_MAT_METAL = 1,   /* color = albedo, param = fuzz */
+  RT_MAT_GLASS = 2,   /* param = ior */
+  RT_MAT_LIGHT = 3,   /* color = emit */
+  RT_MAT_MIXED = 4,   /* child[0] = diff, child[1] = spec, param = weight */
+  RT_MAT_LAYERED = 5  /* child[0] = inner, child[1] = outer (must be RT_MAT_GLASS) */
+};
+
+/* RenderMode — src/camera.ts:13-17 */
+enum { RT_MODE_DEFAULT = 0, RT_MODE_BOUNCES = 1, RT_MODE_SAMPLES = 2 };
+
+/* BVH the device traverses.  REFERENCE = the reference's own median-split topology
+ * (src/geometry/bvh.ts:34-102) walked left-then-right, bit-faithful to its quirks
+ * (inverted boxes of negative-radius spheres, infinite plane boxes, first-visited wins
+ * on equal t).  SAH = binned-SAH tree with near-first ordering: same nearest hits except
+ * for those quirks.  AUTO picks REFERENCE when the scene has a negative-radius sphere
+ * or few objects, SAH otherwise. */
+enum { RT_BVH_AUTO = 0, RT_BVH_REFERENCE = 1, RT_BVH_SAH = 2 };
+
+/* Device integrator layout.  MEGAKERNEL = register-resident paths with per-lane path
+ * regeneration; WAVEFRONT = ray-gen / traverse / per-material shade kernels over path
+ * queues in HBM.  Same estimator, same RNG streams, same image. */
+enum { RT_INTEGRATOR_AUTO = 0, RT_INTEGRATOR_MEGAKERNEL = 1, RT_INTEGRATOR_WAVEFRONT = 2 };
+
+/* CameraData — src/scenes/sceneData.ts:22-37; defaults src/camera.ts:62-71 */
+typedef struct rt_camera_desc {
+  double vfov;
+  double from[3];
+  double at[3];
+  double up[3];
+  double aperture;
+  double focus; /* 0 => |from - at| (src/camera.ts:129) */
+  double background_top[3];
+  double background_bottom[3];
+} rt_camera_desc;
+
+/* SceneData flattened to SoA — src/scenes/sceneData.ts:8-20.  Object order is
+ * SceneData.objects order (it decides BVH tie-breaks and light order). */
+typedef struct rt_scene_desc {
+  uint32_t n_objects;
+  const uint8_t* obj_type;     /* [n_objects] RT_OBJ_* */
+  const double* obj_pos;       /* [n_objects][3] sphere centre | plane/quad corner */
+  const double* obj_u;         /* [n_objects][3] plane/quad u (ignored for spheres) */
+  const double* obj_v;         /* [n_objects][3] plane/quad v */
+  const double* obj_r;         /* [n_objects] sphere radius (may be negative) */
+  const int32_t* obj_material; /* [n_objects] index of the root material node */
+  const uint8_t* obj_light;    /* [n_objects] SceneObject.light flag */
+  uint32_t n_materials;
+  const uint8_t* mat_type;     /* [n_materials] RT_MAT_* */
+  const double* mat_color;     /* [n_materials][3] */
+  const double* mat_param;     /* [n_materials] */
+  const int32_t* mat_child;    /* [n_materials][2], -1 when unused */
+  rt_camera_desc camera;
+} rt_scene_desc;
+
+/* RenderOptions after the reference's three-layer merge (Camera.defaultRenderData <-
+ * sceneData.render <- caller; src/camera.ts:73-83, src/scenes/scenes.ts:97-100) plus the
+ * knobs that exist only on this side of the boundary. */
+typedef struct rt_render_opts {
+  int32_t width;
+  double aspect;
+  int32_t samples;
+  int32_t depth;
+  double a_tolerance;
+  int32_t a_batch;
+  int32_t roulette;       /* bool */
+  int32_t roulette_depth;
+  int32_t mode;           /* RT_MODE_* */
+  /* --- not in the reference --- */
+  uint64_t seed;          /* Philox seed; the reference's Math.random is unseedable */
+  int32_t bvh;            /* RT_BVH_* */
+  int32_t integrator;     /* RT_INTEGRATOR_* */
+  int32_t device;         /* CUDA device ordinal, -1 = current */
+  /* image-space partition for one-process-per-GPU runs: 16x16 tiles, tile k belongs to
+   * part (k + row_shift) % part_count; only owned pixels are rendered/written. */
+  int32_t part_index;     /* 0 <= part_index < part_count */
+  int32_t part_count;     /* <= 1 means the whole region */
+} rt_render_opts;
+
+/* RenderRegion — src/camera.ts:54-59 */
+typedef struct rt_region {
+  int32_t x, y, width, height;
+} rt_region;
+
+/* RenderStats — src/render-utils/renderStats.ts:6-19.  min fields are +Infinity in the
+ * reference when no pixel was rendered; here they are INT32_MAX in that case. */
+typedef struct rt_stats {
+  uint64_t pixels;
+  uint64_t samples_total;
+  int32_t samples_min;
+  int32_t samples_max;
+  uint64_t bounces_total;
+  int32_t bounces_min;
+  int32_t bounces_max;
+  /* --- measurement extras --- */
+  uint64_t rays;        /* closest-hit queries = world.hit calls (src/camera.ts:249) */
+  double device_ms;     /* CUDA-event time of the render kernels on the camera's stream */
+  int32_t kernel_launches; /* kernels of this library launched by the call */
+  int32_t reserved;
+} rt_stats;
+
+/* Derived camera state, for host-side mirrors of the reference's public Camera fields
+ * (src/camera.ts:85-105). */
+typedef struct rt_camera_info {
+  int32_t image_width, image_height, channels;
+  int32_t n_objects, n_lights, n_bvh_nodes, bvh_kind, integrator_kind;
+  float center[3], pixel00_loc[3], pixel_delta_u[3], pixel_delta_v[3];
+  float u[3], v[3], w[3], defocus_disk_u[3], defocus_disk_v[3];
+  double focus_distance;
+  int32_t use_adaptive_sampling;
+  int32_t device;
+  double build_ms; /* host flatten + BVH build + upload */
+} rt_camera_info;
+
+typedef struct rt_camera rt_camera; /* opaque: scene + BVH + options resident on one GPU */
+
+/* ---- lifecycle: replaces createCameraFromSceneData + new Camera(...)
+ *      (src/scenes/scenes.ts:60-104, src/camera.ts:107-166) ---- */
+rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opts, rt_camera** out);
+rt_status rt_camera_destroy(rt_camera* cam);
+rt_status rt_camera_get_info(const rt_camera* cam, rt_camera_info* out);
+
+/* Launch on this CUDA stream (a cudaStream_t passed as void*; NULL = the legacy default
+ * stream).  Lets the host framework time the render with its own events. */
+rt_status rt_camera_set_stream(rt_camera* cam, void* cuda_stream);
+
+/* ---- the hot path: replaces Camera.renderRegion (src/camera.ts:388-431) ----
+ * rgb8: HOST buffer of image_width*image_height*3 bytes, row-major, full-image stride
+ * (offset=(j*W+i)*3, src/camera.ts:461); only pixels inside `region` (and owned by this
+ * part) are written.  linear_rgb: optional HOST float buffer [H][W][3] receiving the
+ * pre-gamma pixel colour (finalColor, src/camera.ts:326-340), or NULL.  Synchronous. */
+rt_status rt_camera_render_region(rt_camera* cam, const rt_region* region, uint8_t* rgb8,
+                                  size_t rgb8_len, float* linear_rgb, rt_stats* stats);
+
+/* replaces Camera.render (src/camera.ts:439-446): the full image. */
+rt_status rt_camera_render(rt_camera* cam, uint8_t* rgb8, size_t rgb8_len, float* linear_rgb,
+                           rt_stats* stats);
+
+/* Same as rt_camera_render_region but rgb8 / linear_rgb / moments are DEVICE pointers on
+ * the camera's device and nothing is copied or synchronised: the call returns once the
+ * kernels are enqueued on the camera's stream.  `moments` (optional, device,
+ * [H][W][8] float) receives per pixel: sum r,g,b, sum r^2,g^2,b^2, samples, bounces.
+ * `stats_dev` (optional, device, sizeof(rt_stats)) receives the reduced statistics
+ * except device_ms. */
+rt_status rt_camera_render_region_device(rt_camera* cam, const rt_region* region, uint8_t* rgb8_dev,
+                                         float* linear_rgb_dev, float* moments_dev,
+                                         rt_stats* stats_dev);
+
+/* Host-buffer render that also returns the per-pixel moments (parity tests). */
+rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint8_t* rgb8,
+                                   size_t rgb8_len, float* linear_rgb, float* moments,
+                                   rt_stats* stats);
+
+/* ---- parity hook: primary visibility through pixel centres (getRay with no jitter and
+ * no defocus, src/camera.ts:176-196) + closest hit over (0.001, inf) (src/camera.ts:249).
+ * HOST outputs, each optional: obj_id [H][W] (index into SceneData.objects, -1 = miss),
+ * t [H][W], normal [H][W][3] (the reference's face-forwarded rec.normal), front_face. */
+rt_status rt_camera_trace_primary(rt_camera* cam, const rt_region* region, int32_t* obj_id,
+                                  float* t, float* normal, uint8_t* front_face);
+
+/* ---- misc ---- */
+const char* rt_last_error(void);
+int32_t rt_device_count(void);
+int32_t rt_abi_version(void);
+/* measured FP32 FMA throughput of `device` in TFLOP/s (dependent-chain FFMA microbenchmark),
+ * the roofline denominator for this path. */
+rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
