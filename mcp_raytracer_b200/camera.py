@@ -1,0 +1,218 @@
+"""Host-side mirror of the reference's `Camera` (src/camera.ts) over the C ABI.
+
+Same names and argument meaning as the reference so callers and tests read alike:
+
+* `Camera(world, cameraOptions, renderData)`      <- src/camera.ts:107-166 (world = SceneData here)
+* `camera.render(pixelData) -> RenderStats`       <- src/camera.ts:439-446
+* `camera.renderRegion(buffer, region)`           <- src/camera.ts:388-431
+* `RenderStats`, `RenderStats.merge`              <- src/render-utils/renderStats.ts:6-64
+* `RenderMode`                                    <- src/camera.ts:13-17
+* `createCameraFromSceneData`, `generateScene`    <- src/scenes/scenes.ts:52-104
+
+All arithmetic happens in the CUDA library; this file only marshals.  `pixelData` is a
+numpy uint8 array of imageWidth*imageHeight*3 bytes (the Uint8ClampedArray of the reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import math
+from typing import Any, Dict, List, Optional
+
+import numpy as np
+
+from . import _native
+from .scene_data import (
+    FlatScene, RaytracerError, merge_render_options, render_opts_struct, rt_camera_info, rt_region, rt_stats,
+)
+from .scenes import generateSceneData
+
+
+class RenderMode(str, enum.Enum):
+    Default = "default"
+    Bounces = "bounces"
+    Samples = "samples"
+
+
+class RenderStats:
+    """src/render-utils/renderStats.ts:6-64"""
+
+    def __init__(self) -> None:
+        self.pixels = 0
+        self.samples = {"total": 0, "min": math.inf, "max": 0, "avg": 0}
+        self.bounces = {"total": 0, "min": math.inf, "max": 0, "avg": 0}
+        # measurement extras (not in the reference)
+        self.rays = 0
+        self.deviceMs = 0.0
+        self.kernelLaunches = 0
+
+    @staticmethod
+    def from_struct(s: rt_stats) -> "RenderStats":
+        r = RenderStats()
+        r.pixels = int(s.pixels)
+        r.samples["total"] = int(s.samples_total)
+        r.bounces["total"] = int(s.bounces_total)
+        if r.pixels > 0:
+            r.samples["min"] = int(s.samples_min)
+            r.samples["max"] = int(s.samples_max)
+            r.bounces["min"] = int(s.bounces_min)
+            r.bounces["max"] = int(s.bounces_max)
+            r.samples["avg"] = r.samples["total"] / r.pixels
+        if r.samples["total"] > 0:
+            r.bounces["avg"] = r.bounces["total"] / r.samples["total"]
+        r.rays = int(s.rays)
+        r.deviceMs = float(s.device_ms)
+        r.kernelLaunches = int(s.kernel_launches)
+        return r
+
+    @staticmethod
+    def merge(stats: List["RenderStats"]) -> "RenderStats":
+        m = RenderStats()
+        for s in stats:
+            m.pixels += s.pixels
+            m.samples["total"] += s.samples["total"]
+            m.samples["min"] = min(m.samples["min"], s.samples["min"])
+            m.samples["max"] = max(m.samples["max"], s.samples["max"])
+            m.bounces["total"] += s.bounces["total"]
+            m.bounces["min"] = min(m.bounces["min"], s.bounces["min"])
+            m.bounces["max"] = max(m.bounces["max"], s.bounces["max"])
+            m.rays += s.rays
+            m.deviceMs = max(m.deviceMs, s.deviceMs)
+            m.kernelLaunches += s.kernelLaunches
+        if m.pixels > 0:
+            m.samples["avg"] = m.samples["total"] / m.pixels
+        if m.samples["total"] > 0:
+            m.bounces["avg"] = m.bounces["total"] / m.samples["total"]
+        return m
+
+
+def _region_struct(region: Optional[Dict[str, int]], W: int, H: int) -> rt_region:
+    if region is None:
+        return rt_region(0, 0, W, H)
+    return rt_region(int(region["x"]), int(region["y"]), int(region["width"]), int(region["height"]))
+
+
+class Camera:
+    channels = 3
+
+    def __init__(self, world: Dict[str, Any], cameraOptions: Optional[Dict[str, Any]] = None,
+                 renderData: Optional[Dict[str, Any]] = None):
+        sceneData = world
+        if cameraOptions:
+            sceneData = dict(world)
+            cam = dict(world.get("camera") or {})
+            cam.update({k: v for k, v in cameraOptions.items() if v is not None})
+            sceneData["camera"] = cam
+        self._flat = FlatScene(sceneData)
+        self.options = merge_render_options(sceneData.get("render"), renderData)
+        self._opts = render_opts_struct(self.options)
+        L = _native.lib()
+        h = C.c_void_p()
+        st = L.rt_camera_create(C.byref(self._flat.desc), C.byref(self._opts), C.byref(h))
+        if st != 0:
+            raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
+        self._h = h
+        info = rt_camera_info()
+        L.rt_camera_get_info(self._h, C.byref(info))
+        self.info = info
+        self.imageWidth = info.image_width
+        self.imageHeight = info.image_height
+        v = lambda a: np.array(list(a), dtype=np.float32)  # noqa: E731
+        self.center, self.pixel00Loc = v(info.center), v(info.pixel00_loc)
+        self.pixelDeltaU, self.pixelDeltaV = v(info.pixel_delta_u), v(info.pixel_delta_v)
+        self.u, self.v, self.w = v(info.u), v(info.v), v(info.w)
+        self.defocusDiskU, self.defocusDiskV = v(info.defocus_disk_u), v(info.defocus_disk_v)
+        self.focusDistance = info.focus_distance
+        self.aperture = float(self._flat.camera.aperture)
+        self.background = {"type": "gradient", "top": list(self._flat.camera.background_top),
+                           "bottom": list(self._flat.camera.background_bottom)}
+        self.useAdaptiveSampling = bool(info.use_adaptive_sampling)
+        self.nLights = info.n_lights
+
+    # -- lifecycle --
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _native.lib().rt_camera_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int) -> None:
+        if st != 0:
+            raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
+
+    def setStream(self, cuda_stream: int) -> None:
+        self._check(_native.lib().rt_camera_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    # -- the hot path --
+    def renderRegion(self, buffer: np.ndarray, region: Optional[Dict[str, int]], linear: Optional[np.ndarray] = None,
+                     moments: Optional[np.ndarray] = None) -> RenderStats:
+        W, H = self.imageWidth, self.imageHeight
+        if buffer is not None:
+            if buffer.dtype != np.uint8 or not buffer.flags["C_CONTIGUOUS"]:
+                raise RaytracerError("pixel buffer must be a C-contiguous uint8 array")
+        reg = _region_struct(region, W, H)
+        st = rt_stats()
+        bp = buffer.ctypes.data if buffer is not None else None
+        bl = buffer.nbytes if buffer is not None else 0
+        lp = linear.ctypes.data if linear is not None else None
+        if linear is not None and (linear.dtype != np.float32 or linear.size < W * H * 3):
+            raise RaytracerError("linear buffer must be float32 [H][W][3]")
+        L = _native.lib()
+        if moments is not None:
+            if moments.dtype != np.float32 or moments.size < W * H * 8:
+                raise RaytracerError("moments buffer must be float32 [H][W][8]")
+            self._check(L.rt_camera_render_moments(self._h, C.byref(reg), bp, bl, lp, moments.ctypes.data, C.byref(st)))
+        else:
+            self._check(L.rt_camera_render_region(self._h, C.byref(reg), bp, bl, lp, C.byref(st)))
+        return RenderStats.from_struct(st)
+
+    def render(self, pixelData: np.ndarray, linear: Optional[np.ndarray] = None) -> RenderStats:
+        return self.renderRegion(pixelData, None, linear)
+
+    def renderRegionDevice(self, region, rgb8_ptr: int = 0, linear_ptr: int = 0, moments_ptr: int = 0, stats_ptr: int = 0) -> None:
+        """Enqueue on the camera's stream; device pointers; no synchronisation."""
+        reg = _region_struct(region, self.imageWidth, self.imageHeight)
+        vp = lambda p: C.c_void_p(p) if p else None  # noqa: E731
+        self._check(_native.lib().rt_camera_render_region_device(self._h, C.byref(reg), vp(rgb8_ptr), vp(linear_ptr),
+                                                                 vp(moments_ptr), vp(stats_ptr)))
+
+    # -- parity hook --
+    def tracePrimary(self, region: Optional[Dict[str, int]] = None):
+        W, H = self.imageWidth, self.imageHeight
+        reg = _region_struct(region, W, H)
+        ids = np.full((H, W), -2, np.int32)
+        t = np.zeros((H, W), np.float32)
+        nrm = np.zeros((H, W, 3), np.float32)
+        ff = np.zeros((H, W), np.uint8)
+        self._check(_native.lib().rt_camera_trace_primary(self._h, C.byref(reg), ids.ctypes.data, t.ctypes.data,
+                                                          nrm.ctypes.data, ff.ctypes.data))
+        return ids, t, nrm, ff
+
+
+def createCameraFromSceneData(sceneData: Dict[str, Any], renderOptions: Optional[Dict[str, Any]] = None) -> Camera:
+    """src/scenes/scenes.ts:60-104"""
+    return Camera(sceneData, None, renderOptions)
+
+
+def generateScene(sceneConfig: Dict[str, Any]) -> Camera:
+    """src/scenes/scenes.ts:52-55"""
+    return createCameraFromSceneData(generateSceneData(sceneConfig), sceneConfig.get("render"))
+
+
+def measureFp32Peak(device: int = -1):
+    t, mhz = C.c_double(), C.c_double()
+    st = _native.lib().rt_measure_fp32_peak(device, C.byref(t), C.byref(mhz))
+    if st != 0:
+        raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
+    return t.value, mhz.value

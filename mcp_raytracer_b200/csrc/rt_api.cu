@@ -1,0 +1,417 @@
+// rt_api.cu — the C ABI of include/rt_b200.h on top of the CUDA kernels.
+//
+// There is NO CPU fallback: without a CUDA device every entry point that would compute
+// returns RT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_scene.h"
+#include "rt_types.h"
+
+namespace rt {
+cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, cudaStream_t st);
+cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* obj_id, float* t, float* normal,
+                                 uint8_t* front, cudaStream_t st);
+cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches, cudaStream_t st);
+} // namespace rt
+
+using namespace rt;
+
+static thread_local std::string g_err;
+static rt_status fail(rt_status st, const std::string& msg) {
+  g_err = msg;
+  return st;
+}
+#define CU(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DeviceGuard { // switch to the camera's device for the duration of a call
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+struct rt_camera {
+  HostScene hs;
+  DevScene ds{};
+  rt_render_opts opts{};
+  int device = 0;
+  int integrator = RT_INTEGRATOR_MEGAKERNEL;
+  cudaStream_t stream = nullptr;
+  double build_ms = 0;
+  // scene buffers
+  std::vector<void*> allocs;
+  // image-sized scratch (lazily allocated, reused across renders)
+  uint8_t* d_rgb8 = nullptr;
+  float* d_linear = nullptr;
+  float* d_moments = nullptr;
+  int32_t* d_ids = nullptr;
+  float* d_t = nullptr;
+  float* d_normal = nullptr;
+  uint8_t* d_front = nullptr;
+  unsigned long long* d_stats = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+template <class T>
+static rt_status upload(rt_camera* c, const std::vector<T>& v, const T** out) {
+  *out = nullptr;
+  if (v.empty()) return RT_OK;
+  void* p = nullptr;
+  CU(cudaMalloc(&p, v.size() * sizeof(T)));
+  c->allocs.push_back(p);
+  CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = (const T*)p;
+  return RT_OK;
+}
+
+static void free_camera(rt_camera* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  for (void* p : c->allocs) cudaFree(p);
+  cudaFree(c->d_rgb8); cudaFree(c->d_linear); cudaFree(c->d_moments); cudaFree(c->d_ids);
+  cudaFree(c->d_t); cudaFree(c->d_normal); cudaFree(c->d_front); cudaFree(c->d_stats);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  delete c;
+}
+
+static rt_status clip_region(const rt_camera* c, const rt_region* r, RenderParams& P) {
+  const int W = c->hs.image_width, H = c->hs.image_height;
+  rt_region full{0, 0, W, H};
+  if (!r) r = &full;
+  if (r->x < 0 || r->y < 0 || r->width < 0 || r->height < 0) return fail(RT_ERR_INVALID_ARGUMENT, "negative region");
+  std::memset(&P, 0, sizeof(P));
+  P.x0 = r->x < W ? r->x : W;
+  P.y0 = r->y < H ? r->y : H;
+  long long x1 = (long long)r->x + r->width, y1 = (long long)r->y + r->height; // camera.ts:390-391
+  P.x1 = (int)(x1 < W ? x1 : W);
+  P.y1 = (int)(y1 < H ? y1 : H);
+  P.part_index = c->opts.part_index;
+  P.part_count = c->opts.part_count;
+  return RT_OK;
+}
+
+static const unsigned long long kStatsInit[kStatCount] = {0, 0, 0, 0, 0x7fffffffull, 0, 0x7fffffffull, 0};
+
+static void unpack_stats(const unsigned long long* raw, rt_stats* s) {
+  s->pixels = raw[kStatPixels];
+  s->samples_total = raw[kStatSamples];
+  s->bounces_total = raw[kStatBounces];
+  s->rays = raw[kStatRays];
+  s->samples_min = (int32_t)raw[kStatSamplesMin];
+  s->samples_max = (int32_t)raw[kStatSamplesMax];
+  s->bounces_min = (int32_t)raw[kStatBouncesMin];
+  s->bounces_max = (int32_t)raw[kStatBouncesMax];
+}
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_err.c_str(); }
+int32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+int32_t rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opts, rt_camera** out) {
+  if (!scene || !opts || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  // validate + compile first: scene errors are reported even on a box without a GPU,
+  // exactly like the reference throws before rendering anything
+  rt_camera* c = new rt_camera();
+  std::string err;
+  rt_status st = compile_scene(scene, opts, c->hs, err);
+  if (st != RT_OK) { delete c; return fail(st, err); }
+  if (opts->part_count > 1 && (opts->part_index < 0 || opts->part_index >= opts->part_count)) {
+    delete c;
+    return fail(RT_ERR_INVALID_ARGUMENT, "part_index out of range");
+  }
+  if (opts->integrator == RT_INTEGRATOR_WAVEFRONT) { delete c; return fail(RT_ERR_UNSUPPORTED, "wavefront integrator not built in this round"); }
+  c->opts = *opts;
+  int ndev = rt_device_count();
+  if (ndev <= 0) { delete c; return fail(RT_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback"); }
+  int dev = opts->device;
+  if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) dev = 0; }
+  if (dev >= ndev) { delete c; return fail(RT_ERR_INVALID_ARGUMENT, "device ordinal out of range"); }
+  c->device = dev;
+  DeviceGuard g(dev);
+  if (!g.ok) { delete c; return fail(RT_ERR_CUDA, "cudaSetDevice failed"); }
+  DevScene& d = c->ds;
+  d.cam = c->hs.cam;
+  const Node* nodes = nullptr;
+#define UP(vec, ptr)                                   \
+  do {                                                 \
+    rt_status s_ = upload(c, vec, ptr);                \
+    if (s_ != RT_OK) { free_camera(c); return s_; }    \
+  } while (0)
+  UP(c->hs.nodes, &nodes);
+  d.nodes = reinterpret_cast<const F4*>(nodes);
+  UP(c->hs.p0, &d.p0); UP(c->hs.p1, &d.p1); UP(c->hs.p2, &d.p2);
+  UP(c->hs.slot_info, &d.slot_info); UP(c->hs.exact, &d.exact);
+  UP(c->hs.matA, &d.matA); UP(c->hs.matB, &d.matB); UP(c->hs.matE, &d.matE);
+  UP(c->hs.lights, &d.lights);
+#undef UP
+  d.n_nodes = (int)c->hs.nodes.size();
+  d.n_slots = (int)c->hs.p0.size();
+  d.n_unbounded = c->hs.n_unbounded;
+  d.n_mats = (int)c->hs.matA.size();
+  d.n_lights = (int)c->hs.lights.size();
+  d.bvh_kind = c->hs.bvh_kind;
+  d.planar_any = c->hs.planar_any;
+  d.seed_lo = (uint32_t)opts->seed;
+  d.seed_hi = (uint32_t)(opts->seed >> 32);
+  if (cudaMalloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+      cudaEventCreate(&c->ev1) != cudaSuccess) {
+    std::string m = cudaGetErrorString(cudaGetLastError());
+    free_camera(c);
+    return fail(RT_ERR_CUDA, "allocating stats/events: " + m);
+  }
+  c->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  *out = c;
+  return RT_OK;
+}
+
+rt_status rt_camera_destroy(rt_camera* cam) {
+  free_camera(cam);
+  return RT_OK;
+}
+
+rt_status rt_camera_get_info(const rt_camera* c, rt_camera_info* o) {
+  if (!c || !o) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  std::memset(o, 0, sizeof(*o));
+  const DevCamera& k = c->hs.cam;
+  o->image_width = c->hs.image_width; o->image_height = c->hs.image_height; o->channels = 3;
+  o->n_objects = c->hs.n_objects; o->n_lights = (int)c->hs.lights.size(); o->n_bvh_nodes = (int)c->hs.nodes.size();
+  o->bvh_kind = c->hs.bvh_kind; o->integrator_kind = c->integrator;
+  std::memcpy(o->center, k.center, 12); std::memcpy(o->pixel00_loc, k.p00, 12);
+  std::memcpy(o->pixel_delta_u, k.du, 12); std::memcpy(o->pixel_delta_v, k.dv, 12);
+  std::memcpy(o->u, c->hs.cam_u, 12); std::memcpy(o->v, c->hs.cam_v, 12); std::memcpy(o->w, c->hs.cam_w, 12);
+  std::memcpy(o->defocus_disk_u, k.ddu, 12); std::memcpy(o->defocus_disk_v, k.ddv, 12);
+  o->focus_distance = c->hs.focus_distance;
+  o->use_adaptive_sampling = k.adaptive;
+  o->device = c->device;
+  o->build_ms = c->build_ms;
+  return RT_OK;
+}
+
+rt_status rt_camera_set_stream(rt_camera* c, void* s) {
+  if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  c->stream = (cudaStream_t)s;
+  return RT_OK;
+}
+
+// enqueue: stats init, render kernel, optional stats finalisation.  No synchronisation.
+static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_dev, int* launches) {
+  CU(cudaMemcpyAsync(c->d_stats, kStatsInit, sizeof(kStatsInit), cudaMemcpyHostToDevice, c->stream));
+  P.stats = c->d_stats;
+  CU(launch_render_mega(c->ds, P, c->stream));
+  *launches = (P.x1 > P.x0 && P.y1 > P.y0) ? 1 : 0;
+  if (stats_dev) {
+    CU(launch_finalize_stats(c->d_stats, stats_dev, *launches + 1, c->stream));
+    *launches += 1;
+  }
+  return RT_OK;
+}
+
+rt_status rt_camera_render_region_device(rt_camera* c, const rt_region* region, uint8_t* rgb8_dev, float* linear_dev,
+                                         float* moments_dev, rt_stats* stats_dev) {
+  if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  DeviceGuard g(c->device);
+  RenderParams P;
+  rt_status st = clip_region(c, region, P);
+  if (st != RT_OK) return st;
+  P.rgb8 = rgb8_dev; P.linear = linear_dev; P.moments = moments_dev;
+  int launches = 0;
+  return enqueue_render(c, P, stats_dev, &launches);
+}
+
+static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb8, size_t rgb8_len, float* linear,
+                             float* moments, rt_stats* stats) {
+  if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  const int W = c->hs.image_width, H = c->hs.image_height;
+  const size_t npx = (size_t)W * H;
+  if (rgb8 && rgb8_len < npx * 3) return fail(RT_ERR_BUFFER_TOO_SMALL, "rgb8 buffer smaller than width*height*3");
+  DeviceGuard g(c->device);
+  RenderParams P;
+  rt_status st = clip_region(c, region, P);
+  if (st != RT_OK) return st;
+  if (rgb8 && !c->d_rgb8) CU(cudaMalloc(&c->d_rgb8, npx * 3));
+  if (linear && !c->d_linear) CU(cudaMalloc(&c->d_linear, npx * 3 * sizeof(float)));
+  if (moments && !c->d_moments) CU(cudaMalloc(&c->d_moments, npx * 8 * sizeof(float)));
+  P.rgb8 = rgb8 ? c->d_rgb8 : nullptr;
+  P.linear = linear ? c->d_linear : nullptr;
+  P.moments = moments ? c->d_moments : nullptr;
+  int launches = 0;
+  CU(cudaEventRecord(c->ev0, c->stream));
+  st = enqueue_render(c, P, nullptr, &launches);
+  if (st != RT_OK) return st;
+  CU(cudaEventRecord(c->ev1, c->stream));
+  unsigned long long raw[kStatCount];
+  CU(cudaMemcpyAsync(raw, c->d_stats, sizeof(raw), cudaMemcpyDeviceToHost, c->stream));
+  const bool whole_tiles = c->opts.part_count <= 1;
+  const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+  if (rw > 0 && rh > 0) {
+    if (whole_tiles) {
+      // only the region's pixels are written (camera.ts:400-401): pitched copies of the sub-rectangle
+      const size_t off = (size_t)P.y0 * W + P.x0;
+      if (rgb8) CU(cudaMemcpy2DAsync(rgb8 + off * 3, (size_t)W * 3, c->d_rgb8 + off * 3, (size_t)W * 3, (size_t)rw * 3, rh, cudaMemcpyDeviceToHost, c->stream));
+      if (linear) CU(cudaMemcpy2DAsync(linear + off * 3, (size_t)W * 12, c->d_linear + off * 3, (size_t)W * 12, (size_t)rw * 12, rh, cudaMemcpyDeviceToHost, c->stream));
+      if (moments) CU(cudaMemcpy2DAsync(moments + off * 8, (size_t)W * 32, c->d_moments + off * 8, (size_t)W * 32, (size_t)rw * 32, rh, cudaMemcpyDeviceToHost, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+    } else {
+      // partitioned render: stage the rows, then copy only the tiles this part owns
+      std::vector<uint8_t> hr;
+      std::vector<float> hl, hm;
+      const size_t row0 = (size_t)P.y0 * W;
+      if (rgb8) { hr.resize((size_t)rh * W * 3); CU(cudaMemcpyAsync(hr.data(), c->d_rgb8 + row0 * 3, hr.size(), cudaMemcpyDeviceToHost, c->stream)); }
+      if (linear) { hl.resize((size_t)rh * W * 3); CU(cudaMemcpyAsync(hl.data(), c->d_linear + row0 * 3, hl.size() * 4, cudaMemcpyDeviceToHost, c->stream)); }
+      if (moments) { hm.resize((size_t)rh * W * 8); CU(cudaMemcpyAsync(hm.data(), c->d_moments + row0 * 8, hm.size() * 4, cudaMemcpyDeviceToHost, c->stream)); }
+      CU(cudaStreamSynchronize(c->stream));
+      for (int y = P.y0; y < P.y1; ++y) {
+        const int ty = y / 16;
+        for (int x = P.x0; x < P.x1;) {
+          const int tx = x / 16;
+          const int xe = std::min(P.x1, (tx + 1) * 16);
+          if ((tx + ty) % c->opts.part_count == c->opts.part_index) {
+            const size_t dst = (size_t)y * W + x, src = (size_t)(y - P.y0) * W + x;
+            const size_t n = (size_t)(xe - x);
+            if (rgb8) std::memcpy(rgb8 + dst * 3, hr.data() + src * 3, n * 3);
+            if (linear) std::memcpy(linear + dst * 3, hl.data() + src * 3, n * 12);
+            if (moments) std::memcpy(moments + dst * 8, hm.data() + src * 8, n * 32);
+          }
+          x = xe;
+        }
+      }
+    }
+  } else {
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  if (stats) {
+    std::memset(stats, 0, sizeof(*stats));
+    unpack_stats(raw, stats);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    stats->device_ms = ms;
+    stats->kernel_launches = launches;
+  }
+  return RT_OK;
+}
+
+rt_status rt_camera_render_region(rt_camera* cam, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
+                                  float* linear_rgb, rt_stats* stats) {
+  return render_host(cam, region, rgb8, rgb8_len, linear_rgb, nullptr, stats);
+}
+rt_status rt_camera_render(rt_camera* cam, uint8_t* rgb8, size_t rgb8_len, float* linear_rgb, rt_stats* stats) {
+  return render_host(cam, nullptr, rgb8, rgb8_len, linear_rgb, nullptr, stats);
+}
+rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
+                                   float* linear_rgb, float* moments, rt_stats* stats) {
+  return render_host(cam, region, rgb8, rgb8_len, linear_rgb, moments, stats);
+}
+
+rt_status rt_camera_trace_primary(rt_camera* c, const rt_region* region, int32_t* obj_id, float* t, float* normal,
+                                  uint8_t* front_face) {
+  if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  DeviceGuard g(c->device);
+  const int W = c->hs.image_width, H = c->hs.image_height;
+  const size_t npx = (size_t)W * H;
+  RenderParams P;
+  rt_status st = clip_region(c, region, P);
+  if (st != RT_OK) return st;
+  if (!c->d_ids) CU(cudaMalloc(&c->d_ids, npx * 4));
+  if (!c->d_t) CU(cudaMalloc(&c->d_t, npx * 4));
+  if (!c->d_normal) CU(cudaMalloc(&c->d_normal, npx * 12));
+  if (!c->d_front) CU(cudaMalloc(&c->d_front, npx));
+  CU(launch_trace_primary(c->ds, P, c->d_ids, c->d_t, c->d_normal, c->d_front, c->stream));
+  const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
+  if (rw > 0 && rh > 0) {
+    const size_t off = (size_t)P.y0 * W + P.x0;
+    if (obj_id) CU(cudaMemcpy2DAsync(obj_id + off, (size_t)W * 4, c->d_ids + off, (size_t)W * 4, (size_t)rw * 4, rh, cudaMemcpyDeviceToHost, c->stream));
+    if (t) CU(cudaMemcpy2DAsync(t + off, (size_t)W * 4, c->d_t + off, (size_t)W * 4, (size_t)rw * 4, rh, cudaMemcpyDeviceToHost, c->stream));
+    if (normal) CU(cudaMemcpy2DAsync(normal + off * 3, (size_t)W * 12, c->d_normal + off * 3, (size_t)W * 12, (size_t)rw * 12, rh, cudaMemcpyDeviceToHost, c->stream));
+    if (front_face) CU(cudaMemcpy2DAsync(front_face + off, (size_t)W, c->d_front + off, (size_t)W, (size_t)rw, rh, cudaMemcpyDeviceToHost, c->stream));
+  }
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+}
+
+rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz) {
+  if (!tflops) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  int ndev = rt_device_count();
+  if (ndev <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device visible");
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  DeviceGuard g(device);
+  int sms = 0, khz = 0;
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+  const int blocks = sms * 16, iters = 2048;
+  float* d = nullptr;
+  CU(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(float)));
+  cudaEvent_t a, b;
+  CU(cudaEventCreate(&a));
+  CU(cudaEventCreate(&b));
+  double best = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CU(cudaEventRecord(a, 0));
+    CU(launch_fp32_peak(d, blocks, iters, 0));
+    CU(cudaEventRecord(b, 0));
+    CU(cudaEventSynchronize(b));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    double flops = (double)blocks * 256.0 * iters * 16.0 * 8.0 * 2.0;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops = best;
+  if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
+  return RT_OK;
+}
+
+} // extern "C"
+
+// ---- tiny device helper: raw stats -> rt_stats on the device (for the no-sync entry point) ----
+namespace rt {
+__global__ void k_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches) {
+  if (threadIdx.x || blockIdx.x) return;
+  rt_stats s;
+  s.pixels = raw[kStatPixels];
+  s.samples_total = raw[kStatSamples];
+  s.bounces_total = raw[kStatBounces];
+  s.rays = raw[kStatRays];
+  s.samples_min = (int32_t)raw[kStatSamplesMin];
+  s.samples_max = (int32_t)raw[kStatSamplesMax];
+  s.bounces_min = (int32_t)raw[kStatBouncesMin];
+  s.bounces_max = (int32_t)raw[kStatBouncesMax];
+  s.device_ms = 0;
+  s.kernel_launches = launches;
+  s.reserved = 0;
+  *out = s;
+}
+cudaError_t launch_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches, cudaStream_t st) {
+  k_finalize_stats<<<1, 32, 0, st>>>(raw, out, launches);
+  return cudaGetLastError();
+}
+} // namespace rt

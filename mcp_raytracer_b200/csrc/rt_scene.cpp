@@ -1,0 +1,546 @@
+// rt_scene.cpp — host scene compiler.
+//
+// Turns the flattened SceneData of include/rt_b200.h into the device layout of rt_types.h:
+// camera block (src/camera.ts:107-166), primitive records with the constructor-time products
+// the reference caches (src/entities/plane.ts:33-42, quad.ts:37, sphere.ts:25-30), material
+// node table with precomputed emission (src/materials/*.ts), light list
+// (src/scenes/scenes.ts:74-79) and one of three acceleration structures:
+//   REFERENCE  the reference's median-split topology (src/geometry/bvh.ts:34-102), flattened;
+//   SAH        binned surface-area-heuristic BVH2 over the bounded primitives, unbounded ones
+//              (infinite planes) kept in an always-tested prefix;
+//   LIST       no hierarchy, object order (tiny scenes: the reference's Cornell BVH degenerates
+//              to "all 8 primitives behind 3 box tests").
+//
+// Host arithmetic follows the reference's numeric model where values are handed to the
+// device as data: vectors are rounded to FP32 after every vector op, scalars stay FP64.
+#include "rt_scene.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <limits>
+#include <numeric>
+
+namespace rt {
+namespace {
+
+const double kInfD = std::numeric_limits<double>::infinity();
+const double kPiD = 3.141592653589793;
+
+// FP32-stored 3-vector with FP64 evaluation (gl-matrix Float32Array semantics).
+struct H3 {
+  float v[3];
+  float& operator[](int i) { return v[i]; }
+  float operator[](int i) const { return v[i]; }
+};
+template <class F>
+H3 map3(F f) {
+  H3 r;
+  for (int i = 0; i < 3; ++i) r.v[i] = (float)f(i);
+  return r;
+}
+H3 from_d(const double* p) { return map3([&](int i) { return p[i]; }); }
+H3 vsum(const H3& a, const H3& b) { return map3([&](int i) { return (double)a[i] + (double)b[i]; }); }
+H3 vdiff(const H3& a, const H3& b) { return map3([&](int i) { return (double)a[i] - (double)b[i]; }); }
+H3 vtimes(const H3& a, double s) { return map3([&](int i) { return (double)a[i] * s; }); }
+H3 vover(const H3& a, double t) { return vtimes(a, 1.0 / t); }
+double vdot(const H3& a, const H3& b) { return (double)a[0] * b[0] + (double)a[1] * b[1] + (double)a[2] * b[2]; }
+H3 vcross(const H3& a, const H3& b) {
+  return map3([&](int i) {
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    return (double)a[j] * b[k] - (double)a[k] * b[j];
+  });
+}
+H3 vnormalize(const H3& a) {
+  double l = vdot(a, a);
+  if (l > 0) l = 1.0 / std::sqrt(l);
+  return vtimes(a, l);
+}
+H3 vnegate(const H3& a) {
+  return map3([&](int i) { double x = -(double)a[i]; return x == 0 ? 0.0 : x; });
+}
+void put3(float* dst, const H3& a) { dst[0] = a[0]; dst[1] = a[1]; dst[2] = a[2]; }
+
+struct Box {
+  float mn[3], mx[3];
+};
+Box empty_box() {
+  Box b;
+  for (int i = 0; i < 3; ++i) { b.mn[i] = (float)kInfD; b.mx[i] = (float)-kInfD; }
+  return b;
+}
+Box merge(const Box& a, const Box& b) { // aabb.ts:68-80 (min/max of FP32 values is exact)
+  Box r;
+  for (int i = 0; i < 3; ++i) { r.mn[i] = std::min(a.mn[i], b.mn[i]); r.mx[i] = std::max(a.mx[i], b.mx[i]); }
+  return r;
+}
+bool finite_box(const Box& b) {
+  for (int i = 0; i < 3; ++i)
+    if (!std::isfinite(b.mn[i]) || !std::isfinite(b.mx[i])) return false;
+  return true;
+}
+
+// One object with everything its reference constructor computes.
+struct Prim {
+  int type = 0, obj = 0, mat = 0;
+  H3 q{}, u{}, v{}, n{}, w{};
+  double r = 0, D = 0, area = 0;
+  Box ref_box; // exactly the reference's boundingBox()
+  Box sah_box; // finite and non-inverted where possible
+  bool bounded = true;
+  F4 rec0{}, rec1{}, rec2{};
+};
+
+void make_sphere(Prim& p) {
+  H3 rv = map3([&](int) { return p.r; }); // Vec3.create(r,r,r), sphere.ts:26
+  H3 lo = vdiff(p.q, rv), hi = vsum(p.q, rv);
+  for (int i = 0; i < 3; ++i) {
+    p.ref_box.mn[i] = lo[i];
+    p.ref_box.mx[i] = hi[i];
+    p.sah_box.mn[i] = std::min(lo[i], hi[i]);
+    p.sah_box.mx[i] = std::max(lo[i], hi[i]);
+  }
+  p.bounded = finite_box(p.sah_box);
+  p.rec0 = F4{p.q[0], p.q[1], p.q[2], (float)p.r};
+}
+
+void make_planar(Prim& p) {
+  H3 cp = vcross(p.u, p.v); // plane.ts:33-42
+  p.n = vnormalize(cp);
+  p.D = vdot(p.n, p.q);
+  p.w = vover(cp, vdot(cp, cp));
+  const double eps = 1e-4;
+  if (p.type == OBJ_PLANE) { // plane.ts:122-154
+    Box b;
+    for (int i = 0; i < 3; ++i) { b.mn[i] = (float)-kInfD; b.mx[i] = (float)kInfD; }
+    for (int ax = 0; ax < 3; ++ax) {
+      if (std::fabs((double)p.n[ax]) > 0.9999) {
+        double c = p.D / (double)p.n[ax];
+        b.mn[ax] = (float)(c - eps);
+        b.mx[ax] = (float)(c + eps);
+        break;
+      }
+    }
+    p.ref_box = b;
+    p.sah_box = b;
+    p.bounded = false;
+  } else { // quad.ts:92-114
+    p.area = std::hypot((double)cp[0], (double)cp[1], (double)cp[2]);
+    H3 c1 = p.q, c2 = vsum(p.q, p.u), c3 = vsum(p.q, p.v), c4 = vsum(vsum(p.q, p.u), p.v);
+    for (int i = 0; i < 3; ++i) {
+      double lo = std::min(std::min((double)c1[i], (double)c2[i]), std::min((double)c3[i], (double)c4[i]));
+      double hi = std::max(std::max((double)c1[i], (double)c2[i]), std::max((double)c3[i], (double)c4[i]));
+      p.ref_box.mn[i] = (float)(lo - eps);
+      p.ref_box.mx[i] = (float)(hi + eps);
+    }
+    p.sah_box = p.ref_box;
+    p.bounded = finite_box(p.sah_box);
+  }
+  // alpha = w.(hp x v) = hp.(v x w); beta = w.(u x hp) = hp.(w x u)   (plane.ts:71-74)
+  double nn[3] = {p.n[0], p.n[1], p.n[2]};
+  double A[3], B[3];
+  double vv[3] = {p.v[0], p.v[1], p.v[2]}, uu[3] = {p.u[0], p.u[1], p.u[2]}, ww[3] = {p.w[0], p.w[1], p.w[2]},
+         qq[3] = {p.q[0], p.q[1], p.q[2]};
+  for (int i = 0; i < 3; ++i) {
+    int j = (i + 1) % 3, k = (i + 2) % 3;
+    A[i] = vv[j] * ww[k] - vv[k] * ww[j];
+    B[i] = ww[j] * uu[k] - ww[k] * uu[j];
+  }
+  double a0 = qq[0] * A[0] + qq[1] * A[1] + qq[2] * A[2];
+  double b0 = qq[0] * B[0] + qq[1] * B[1] + qq[2] * B[2];
+  p.rec0 = F4{(float)nn[0], (float)nn[1], (float)nn[2], (float)p.D};
+  p.rec1 = F4{(float)A[0], (float)A[1], (float)A[2], (float)a0};
+  p.rec2 = F4{(float)B[0], (float)B[1], (float)B[2], (float)b0};
+}
+
+// ---- build tree (shared by both builders) ----
+struct BNode {
+  Box box;
+  int left = -1, right = -1; // indices into the BNode pool; -1 = none
+  std::vector<int> prims;    // leaf: ordered primitive indices
+  bool leaf = false;
+};
+
+struct RefBuilder { // src/geometry/bvh.ts:34-102
+  const std::vector<Prim>& P;
+  std::vector<BNode>& pool;
+  int build(const std::vector<int>& objects, size_t start, size_t end) {
+    std::vector<int> list(objects.begin() + start, objects.begin() + end);
+    Box nb = P[list[0]].ref_box;
+    for (size_t i = 1; i < list.size(); ++i) nb = merge(nb, P[list[i]].ref_box);
+    double ex = (double)nb.mx[0] - (double)nb.mn[0];
+    double ey = (double)nb.mx[1] - (double)nb.mn[1];
+    double ez = (double)nb.mx[2] - (double)nb.mn[2];
+    int axis = 0;
+    if (ey > ex && ey > ez) axis = 1;
+    else if (ez > ex && ez > ey) axis = 2;
+    size_t span = end - start;
+    BNode node;
+    auto less_on_axis = [&](int a, int b) { return P[a].ref_box.mn[axis] < P[b].ref_box.mn[axis]; };
+    if (span <= 4) {
+      node.leaf = true;
+      if (span == 2 && !less_on_axis(list[0], list[1])) std::swap(list[0], list[1]);
+      node.prims = list;
+      // box = surroundingBox(left.box, right.box): fold of the members (empty box is the identity)
+      Box b = empty_box();
+      for (int pi : list) b = merge(b, P[pi].ref_box);
+      node.box = b;
+      pool.push_back(node);
+      return (int)pool.size() - 1;
+    }
+    // Array.prototype.sort with a comparator that only ever says "<0" or ">0": V8's TimSort
+    // consults nothing but `order < 0`, which makes it a stable sort on `<`.
+    std::stable_sort(list.begin(), list.end(), less_on_axis);
+    size_t mid = span / 2;
+    int l = build(list, 0, mid);
+    int r = build(list, mid, span);
+    node.left = l;
+    node.right = r;
+    node.box = merge(pool[l].box, pool[r].box);
+    pool.push_back(node);
+    return (int)pool.size() - 1;
+  }
+};
+
+struct SahBuilder {
+  const std::vector<Prim>& P;
+  std::vector<BNode>& pool;
+  static double area(const Box& b) {
+    double dx = (double)b.mx[0] - b.mn[0], dy = (double)b.mx[1] - b.mn[1], dz = (double)b.mx[2] - b.mn[2];
+    if (dx < 0 || dy < 0 || dz < 0) return 0;
+    return 2 * (dx * dy + dy * dz + dz * dx);
+  }
+  int make_leaf(const std::vector<int>& idx, size_t b, size_t e) {
+    BNode n;
+    n.leaf = true;
+    n.box = empty_box();
+    for (size_t i = b; i < e; ++i) { n.prims.push_back(idx[i]); n.box = merge(n.box, P[idx[i]].sah_box); }
+    pool.push_back(n);
+    return (int)pool.size() - 1;
+  }
+  int build(std::vector<int>& idx, size_t b, size_t e, int depth) {
+    size_t n = e - b;
+    if (n <= 2) return make_leaf(idx, b, e);
+    Box bounds = empty_box(), cb = empty_box();
+    auto centroid = [&](int pi, int ax) { return 0.5f * (P[pi].sah_box.mn[ax] + P[pi].sah_box.mx[ax]); };
+    for (size_t i = b; i < e; ++i) {
+      bounds = merge(bounds, P[idx[i]].sah_box);
+      for (int ax = 0; ax < 3; ++ax) {
+        float c = centroid(idx[i], ax);
+        cb.mn[ax] = std::min(cb.mn[ax], c);
+        cb.mx[ax] = std::max(cb.mx[ax], c);
+      }
+    }
+    const int NB = 16;
+    double best_cost = std::numeric_limits<double>::infinity();
+    int best_axis = -1, best_split = -1;
+    for (int ax = 0; ax < 3; ++ax) {
+      float lo = cb.mn[ax], hi = cb.mx[ax];
+      if (!(hi > lo)) continue;
+      Box bb[NB];
+      int cnt[NB];
+      for (int k = 0; k < NB; ++k) { bb[k] = empty_box(); cnt[k] = 0; }
+      float scale = NB / (hi - lo);
+      for (size_t i = b; i < e; ++i) {
+        int k = std::min(NB - 1, std::max(0, (int)((centroid(idx[i], ax) - lo) * scale)));
+        cnt[k]++;
+        bb[k] = merge(bb[k], P[idx[i]].sah_box);
+      }
+      double ra[NB];
+      int rc[NB];
+      Box acc = empty_box();
+      int c = 0;
+      for (int k = NB - 1; k >= 1; --k) { acc = merge(acc, bb[k]); c += cnt[k]; ra[k] = area(acc); rc[k] = c; }
+      acc = empty_box();
+      c = 0;
+      for (int k = 0; k < NB - 1; ++k) {
+        acc = merge(acc, bb[k]);
+        c += cnt[k];
+        if (c == 0 || rc[k + 1] == 0) continue;
+        double cost = area(acc) * c + ra[k + 1] * rc[k + 1];
+        if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = k; }
+      }
+    }
+    size_t mid;
+    if (best_axis < 0 || depth > 56) {
+      if (n <= 4) return make_leaf(idx, b, e);
+      // degenerate centroids (or a runaway depth): median split on the widest axis
+      int ax = 0;
+      float w = -1;
+      for (int a = 0; a < 3; ++a) { float d = bounds.mx[a] - bounds.mn[a]; if (d > w) { w = d; ax = a; } }
+      mid = b + n / 2;
+      std::nth_element(idx.begin() + b, idx.begin() + mid, idx.begin() + e,
+                       [&](int x, int y) { return centroid(x, ax) < centroid(y, ax); });
+    } else {
+      if (n <= 4) {
+        // leaf cost (n prim tests) vs split cost (2 box tests + expected prim tests)
+        double leaf_cost = (double)n;
+        double split_cost = 1.2 + best_cost / std::max(area(bounds), 1e-30);
+        if (leaf_cost <= split_cost) return make_leaf(idx, b, e);
+      }
+      float lo = cb.mn[best_axis], hi = cb.mx[best_axis];
+      float scale = NB / (hi - lo);
+      auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](int pi) {
+        int k = std::min(NB - 1, std::max(0, (int)((centroid(pi, best_axis) - lo) * scale)));
+        return k <= best_split;
+      });
+      mid = (size_t)(it - idx.begin());
+      if (mid == b || mid == e) mid = b + n / 2;
+    }
+    int l = build(idx, b, mid, depth + 1);
+    int r = build(idx, mid, e, depth + 1);
+    BNode node;
+    node.left = l;
+    node.right = r;
+    node.box = merge(pool[l].box, pool[r].box);
+    pool.push_back(node);
+    return (int)pool.size() - 1;
+  }
+};
+
+struct Flattener {
+  const std::vector<Prim>& P;
+  const std::vector<BNode>& pool;
+  HostScene& S;
+  int max_depth = 0;
+  void push_slot(int pi) {
+    const Prim& p = P[pi];
+    S.p0.push_back(p.rec0);
+    S.p1.push_back(p.rec1);
+    S.p2.push_back(p.rec2);
+    S.slot_info.push_back(I2{p.mat, p.obj | (p.type << 30)});
+    ExactPrim e;
+    std::memset(&e, 0, sizeof(e));
+    put3(e.q, p.q); put3(e.u, p.u); put3(e.v, p.v); put3(e.n, p.n); put3(e.w, p.w);
+    e.type = p.type; e.D = p.D; e.r = p.r; e.area = p.area;
+    S.exact.push_back(e);
+  }
+  int leaf_ref(const BNode& n) {
+    int first = (int)S.p0.size();
+    int mask = 0;
+    for (size_t k = 0; k < n.prims.size(); ++k) {
+      if (P[n.prims[k]].type != OBJ_SPHERE) mask |= 1 << k;
+      push_slot(n.prims[k]);
+    }
+    return make_leaf_ref(first, (int)n.prims.size(), mask);
+  }
+  int emit(int bi, int depth) { // returns the child ref for build node bi
+    const BNode& n = pool[bi];
+    max_depth = std::max(max_depth, depth);
+    if (n.leaf) return leaf_ref(n);
+    int idx = (int)S.nodes.size();
+    S.nodes.emplace_back();
+    fill_pair(idx, n.left, n.right, depth);
+    return idx;
+  }
+  void fill_pair(int idx, int l, int r, int depth) {
+    Node nd;
+    std::memset(&nd, 0, sizeof(nd));
+    Box lb = l >= 0 ? pool[l].box : empty_box();
+    Box rb = r >= 0 ? pool[r].box : empty_box();
+    std::memcpy(nd.lmin, lb.mn, 12); std::memcpy(nd.lmax, lb.mx, 12);
+    std::memcpy(nd.rmin, rb.mn, 12); std::memcpy(nd.rmax, rb.mx, 12);
+    nd.left = l >= 0 ? emit(l, depth + 1) : kEmptyRef;
+    nd.right = r >= 0 ? emit(r, depth + 1) : kEmptyRef;
+    S.nodes[idx] = nd;
+  }
+};
+
+} // namespace
+
+rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostScene& S, std::string& err) {
+  if (!sd || !o) { err = "null scene or options"; return RT_ERR_INVALID_ARGUMENT; }
+  if (sd->n_objects == 0 || !sd->obj_type || !sd->obj_pos || !sd->obj_material) {
+    err = "scene has no objects";
+    return RT_ERR_INVALID_ARGUMENT;
+  }
+  if (sd->n_objects > (1u << 24)) { err = "too many objects (max 2^24)"; return RT_ERR_UNSUPPORTED; }
+  if (o->width <= 0 || !(o->aspect > 0) || o->samples < 0 || o->depth < 0 || o->a_batch <= 0) {
+    err = "invalid render options (width/aspect/samples/depth/aBatch)";
+    return RT_ERR_INVALID_ARGUMENT;
+  }
+  // ---- materials (createMaterial, scenes.ts:144-199) ----
+  const uint32_t nm = sd->n_materials;
+  S.matA.resize(nm); S.matB.resize(nm); S.matE.resize(nm);
+  for (uint32_t i = 0; i < nm; ++i) {
+    int ty = sd->mat_type[i];
+    const double* c = sd->mat_color + 3 * (size_t)i;
+    double prm = sd->mat_param[i];
+    int c0 = sd->mat_child ? sd->mat_child[2 * i] : -1, c1 = sd->mat_child ? sd->mat_child[2 * i + 1] : -1;
+    H3 col = from_d(c);
+    H3 emit = map3([](int) { return 0.0; });
+    auto child_ok = [&](int ci) { return ci >= 0 && (uint32_t)ci < i; }; // children precede parents => acyclic
+    switch (ty) {
+      case MAT_LAMBERT: break;
+      case MAT_METAL: prm = prm < 1 ? std::max(0.0, prm) : 1; break; // metal.ts:20
+      case MAT_GLASS: break;
+      case MAT_LIGHT: emit = col; break; // diffuseLight.ts:29-31
+      case MAT_MIXED: {
+        if (!child_ok(c0) || !child_ok(c1)) { err = "Material not found: " + std::to_string(!child_ok(c0) ? c0 : c1); return RT_ERR_MATERIAL_NOT_FOUND; }
+        prm = std::max(0.0, std::min(1.0, prm)); // mixedMaterial.ts:29
+        H3 e1{{S.matE[c0].x, S.matE[c0].y, S.matE[c0].z}}, e2{{S.matE[c1].x, S.matE[c1].y, S.matE[c1].z}};
+        emit = vsum(vtimes(e1, prm), vtimes(e2, 1.0 - prm)); // mixedMaterial.ts:52-57
+        break;
+      }
+      case MAT_LAYERED: {
+        if (!child_ok(c1)) { err = "Material not found: " + std::to_string(c1); return RT_ERR_MATERIAL_NOT_FOUND; }
+        if (sd->mat_type[c1] != MAT_GLASS) { err = "Material is not a dielectric: " + std::to_string(c1); return RT_ERR_NOT_DIELECTRIC; }
+        if (!child_ok(c0)) { err = "Material not found: " + std::to_string(c0); return RT_ERR_MATERIAL_NOT_FOUND; }
+        prm = sd->mat_param[c1];                                        // outer ior
+        emit = H3{{S.matE[c0].x, S.matE[c0].y, S.matE[c0].z}};          // layeredMaterial.ts:61-63
+        break;
+      }
+      default: err = "Unknown material type: " + std::to_string(ty); return RT_ERR_UNKNOWN_MATERIAL_TYPE;
+    }
+    bool has_e = emit[0] != 0 || emit[1] != 0 || emit[2] != 0;
+    S.matA[i] = F4{col[0], col[1], col[2], (float)prm};
+    S.matB[i] = I4{ty, c0, c1, has_e ? 1 : 0};
+    S.matE[i] = F4{emit[0], emit[1], emit[2], has_e ? 1.f : 0.f};
+  }
+  // ---- objects (createSceneObject, scenes.ts:109-139) ----
+  const uint32_t n = sd->n_objects;
+  std::vector<Prim> P(n);
+  bool any_negative = false, any_unbounded = false;
+  S.planar_any = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    Prim& p = P[i];
+    int mi = sd->obj_material[i];
+    if (mi < 0 || (uint32_t)mi >= nm) { err = "Material not found: " + std::to_string(mi); return RT_ERR_MATERIAL_NOT_FOUND; }
+    p.obj = (int)i;
+    p.mat = mi;
+    p.type = sd->obj_type[i];
+    p.q = from_d(sd->obj_pos + 3 * (size_t)i);
+    if (p.type == OBJ_SPHERE) {
+      p.r = sd->obj_r ? sd->obj_r[i] : 0;
+      if (p.r < 0) any_negative = true;
+      make_sphere(p);
+    } else if (p.type == OBJ_PLANE || p.type == OBJ_QUAD) {
+      if (!sd->obj_u || !sd->obj_v) { err = "plane/quad without u/v"; return RT_ERR_INVALID_ARGUMENT; }
+      p.u = from_d(sd->obj_u + 3 * (size_t)i);
+      p.v = from_d(sd->obj_v + 3 * (size_t)i);
+      make_planar(p);
+      S.planar_any = 1;
+    } else {
+      err = "Unknown object type: " + std::to_string(p.type);
+      return RT_ERR_UNKNOWN_OBJECT_TYPE;
+    }
+    if (!p.bounded) any_unbounded = true;
+  }
+  S.n_objects = (int)n;
+  // ---- lights (scenes.ts:74-79): light:true AND has a `pdf` method (Sphere, Quad) ----
+  for (uint32_t i = 0; i < n; ++i) {
+    if (!(sd->obj_light && sd->obj_light[i])) continue;
+    const Prim& p = P[i];
+    if (p.type != OBJ_SPHERE && p.type != OBJ_QUAD) continue;
+    DevLight L;
+    std::memset(&L, 0, sizeof(L));
+    L.p0 = p.rec0; L.p1 = p.rec1; L.p2 = p.rec2;
+    put3(L.q, p.q); put3(L.u, p.u); put3(L.v, p.v);
+    L.area = (float)p.area;
+    L.radius = (float)p.r;
+    L.type = p.type;
+    L.slot = (int)i; // object index; resolved to a slot below
+    S.lights.push_back(L);
+  }
+  // ---- acceleration structure ----
+  int kind = o->bvh;
+  if (kind == RT_BVH_AUTO) {
+    if (any_negative) kind = BVH_REFERENCE;      // inverted boxes are only meaningful in the reference topology
+    else if (n <= 16) kind = BVH_LIST;
+    else kind = BVH_SAH;
+  }
+  if (kind != BVH_REFERENCE && kind != BVH_SAH && kind != BVH_LIST) { err = "invalid bvh kind"; return RT_ERR_INVALID_ARGUMENT; }
+  if (kind == BVH_LIST && n > 64) { err = "RT_BVH_LIST supports at most 64 objects"; return RT_ERR_UNSUPPORTED; }
+  S.bvh_kind = kind;
+  S.n_unbounded = 0;
+  std::vector<BNode> pool;
+  Flattener fl{P, pool, S};
+  if (kind == BVH_LIST) {
+    // Same visiting order as the reference's tree (left-to-right over its leaves) so that
+    // exact-t ties resolve to the same primitive; only the box tests are dropped, which
+    // cannot change a nearest hit when no box is inverted.
+    pool.reserve(n);
+    std::vector<int> all(n);
+    std::iota(all.begin(), all.end(), 0);
+    RefBuilder rb{P, pool};
+    int root = rb.build(all, 0, n);
+    std::function<void(int)> walk = [&](int bi) {
+      const BNode& b = pool[bi];
+      if (b.leaf) { for (int pi : b.prims) fl.push_slot(pi); return; }
+      walk(b.left);
+      walk(b.right);
+    };
+    walk(root);
+    S.n_unbounded = (int)n; // every slot is "always tested"
+  } else if (kind == BVH_REFERENCE) {
+    pool.reserve(n);
+    std::vector<int> all(n);
+    std::iota(all.begin(), all.end(), 0);
+    RefBuilder rb{P, pool};
+    int root = rb.build(all, 0, n);
+    // node 0 = super-root: the reference tests the root's own box first (bvh.ts:130)
+    S.nodes.emplace_back();
+    fl.fill_pair(0, root, -1, 0);
+  } else {
+    std::vector<int> bounded;
+    for (uint32_t i = 0; i < n; ++i) {
+      if (P[i].bounded) bounded.push_back((int)i);
+      else fl.push_slot((int)i);
+    }
+    S.n_unbounded = (int)S.p0.size();
+    (void)any_unbounded;
+    if (!bounded.empty()) {
+      pool.reserve(bounded.size());
+      SahBuilder sb{P, pool};
+      int root = sb.build(bounded, 0, bounded.size(), 0);
+      S.nodes.emplace_back();
+      if (pool[root].leaf) fl.fill_pair(0, root, -1, 0);
+      else fl.fill_pair(0, pool[root].left, pool[root].right, 0);
+    }
+  }
+  S.max_depth = fl.max_depth;
+  if (S.max_depth > 60) { err = "BVH too deep"; return RT_ERR_UNSUPPORTED; }
+  // resolve light slots
+  {
+    std::vector<int> obj_to_slot(n, -1);
+    for (size_t s = 0; s < S.slot_info.size(); ++s) obj_to_slot[S.slot_info[s].y & 0x3fffffff] = (int)s;
+    for (auto& L : S.lights) L.slot = obj_to_slot[L.slot];
+  }
+  // ---- camera (camera.ts:107-166) ----
+  const rt_camera_desc& c = sd->camera;
+  DevCamera& cam = S.cam;
+  std::memset(&cam, 0, sizeof(cam));
+  S.image_width = o->width;
+  S.image_height = (int)std::ceil((double)o->width / o->aspect);
+  if (S.image_height <= 0 || (double)S.image_width * S.image_height > 2147483647.0) { err = "image too large"; return RT_ERR_INVALID_ARGUMENT; }
+  H3 from = from_d(c.from), at = from_d(c.at), up = from_d(c.up);
+  double focus = (c.focus != 0 && !std::isnan(c.focus)) ? c.focus : [&] { H3 d = vdiff(from, at); return std::hypot((double)d[0], (double)d[1], (double)d[2]); }();
+  double theta = c.vfov * (kPiD / 180);
+  double h = std::tan(theta / 2);
+  double vh = 2 * h * focus;
+  double ar = (double)S.image_width / S.image_height;
+  double vw = vh * ar;
+  H3 w = vnormalize(vdiff(from, at));
+  H3 u = vnormalize(vcross(up, w));
+  H3 v = vcross(w, u);
+  H3 viewportU = vtimes(u, vw), viewportV = vtimes(v, -vh);
+  H3 du = vover(viewportU, S.image_width), dv = vover(viewportV, S.image_height);
+  H3 ul = vdiff(vdiff(vdiff(from, vtimes(w, focus)), vover(viewportU, 2)), vover(viewportV, 2));
+  H3 p00 = vsum(ul, vtimes(vsum(du, dv), 0.5));
+  H3 ddu = vtimes(u, c.aperture / 2), ddv = vtimes(v, c.aperture / 2);
+  put3(cam.center, from); put3(cam.p00, p00); put3(cam.du, du); put3(cam.dv, dv); put3(cam.ddu, ddu); put3(cam.ddv, ddv);
+  put3(cam.bg_top, from_d(c.background_top)); put3(cam.bg_bottom, from_d(c.background_bottom));
+  put3(S.cam_u, u); put3(S.cam_v, v); put3(S.cam_w, w);
+  S.focus_distance = focus;
+  cam.width = S.image_width; cam.height = S.image_height;
+  cam.samples = o->samples; cam.depth = o->depth; cam.rr_depth = o->roulette_depth; cam.a_batch = o->a_batch;
+  cam.mode = o->mode; cam.a_tol = (float)o->a_tolerance;
+  cam.roulette = o->roulette != 0;
+  cam.adaptive = (o->a_tolerance > 0 && o->samples > 1) ? 1 : 0; // camera.ts:165
+  cam.jitter = o->samples > 1;                                    // camera.ts:184
+  cam.defocus = c.aperture > 0;                                   // camera.ts:197
+  return RT_OK;
+}
+
+} // namespace rt

@@ -1,0 +1,112 @@
+// rt_types.h — POD layouts shared by the host scene compiler and the sm_100a kernels.
+//
+// Data layout in HBM (all arrays 16-byte aligned, read-only during a render):
+//   nodes   [n_nodes]  4 x float4 = 64 B   two child boxes + two child refs (pair layout)
+//   p0      [n_slots]  float4              sphere: (cx,cy,cz,r) | planar: (nx,ny,nz,D)
+//   p1,p2   [n_slots]  float4              planar only: (A.xyz, q.A) and (B.xyz, q.B) with
+//                                          A = v x w, B = w x u  =>  alpha = p.A - q.A,
+//                                          beta = p.B - q.B  (plane.ts:71-74 rewritten by the
+//                                          scalar-triple-product identity)
+//   slot_info [n_slots] int2               (material root, original object index | type<<30)
+//   exact   [n_slots]  ExactPrim 96 B      FP32 vectors + FP64 scalars exactly as the reference
+//                                          holds them; touched only by the guarded FP64 re-test
+//   matA    [n_mats]   float4              (r,g,b,param)
+//   matB    [n_mats]   int4                (type, child0, child1, has_emission)
+//   matE    [n_mats]   float4              precomputed emitted() of the subtree rooted here
+//   lights  [n_lights] DevLight
+// Slots are primitives in BVH-leaf order, so a leaf is a contiguous slot range.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define RT_HD __host__ __device__
+#else
+#define RT_HD
+#endif
+
+namespace rt {
+
+enum : int { OBJ_SPHERE = 0, OBJ_PLANE = 1, OBJ_QUAD = 2 };
+enum : int { MAT_LAMBERT = 0, MAT_METAL = 1, MAT_GLASS = 2, MAT_LIGHT = 3, MAT_MIXED = 4, MAT_LAYERED = 5 };
+enum : int { BVH_REFERENCE = 1, BVH_SAH = 2, BVH_LIST = 3 };
+
+struct F4 { float x, y, z, w; };
+struct I4 { int x, y, z, w; };
+struct I2 { int x, y; };
+
+// Child reference encoding: >= 0 internal node index; < 0 leaf with v = ~ref:
+//   first slot = v >> 6, count = ((v >> 4) & 3) + 1, planar mask = v & 15.
+// kEmptyRef marks a child that is never entered (its box is inverted as well).
+static const int kEmptyRef = 0x7fffffff;
+RT_HD inline int make_leaf_ref(int first, int count, int planar_mask) {
+  return ~((first << 6) | ((count - 1) << 4) | (planar_mask & 15));
+}
+
+struct alignas(16) Node { // 64 B
+  float lmin[3], lmax[3];
+  float rmin[3], rmax[3];
+  int left, right;
+  int pad0, pad1;
+};
+
+struct alignas(16) ExactPrim { // 96 B
+  float q[3];  // sphere centre | planar corner
+  float u[3], v[3], n[3], w[3];
+  int type;
+  double D;    // plane.ts:39
+  double r;    // sphere radius (JS double)
+  double area; // quad.ts:37
+};
+
+struct alignas(16) DevLight { // light = object with light:true that is a Sphere or a Quad (scenes.ts:74-79)
+  F4 p0, p1, p2;  // same records as the slot arrays
+  float q[3], u[3], v[3];
+  float area;     // quad
+  float radius;   // sphere
+  int type;
+  int slot;
+  int pad;
+};
+
+struct DevCamera {
+  float center[3], p00[3], du[3], dv[3], ddu[3], ddv[3];
+  float bg_top[3], bg_bottom[3];
+  int width, height;
+  int samples, depth, rr_depth, a_batch, mode;
+  float a_tol;
+  int roulette, adaptive, jitter, defocus;
+};
+
+struct DevScene {
+  DevCamera cam;
+  const F4* nodes; // 4 per node
+  const F4* p0;
+  const F4* p1;
+  const F4* p2;
+  const I2* slot_info;
+  const ExactPrim* exact;
+  const F4* matA;
+  const I4* matB;
+  const F4* matE;
+  const DevLight* lights;
+  int n_nodes, n_slots, n_unbounded, n_mats, n_lights;
+  int bvh_kind;
+  int planar_any; // scene has planes/quads
+  uint32_t seed_lo, seed_hi;
+};
+
+// Per-render launch parameters.
+struct RenderParams {
+  int x0, y0, x1, y1;          // region, clipped to the image
+  int part_index, part_count;  // diagonal 16x16 tile interleave; owner = (tx + ty) % part_count
+  uint8_t* rgb8;               // [H][W][3] or null
+  float* linear;               // [H][W][3] or null
+  float* moments;              // [H][W][8] or null
+  unsigned long long* stats;   // device RenderStats accumulator (see kStat*)
+};
+enum : int {
+  kStatPixels = 0, kStatSamples, kStatBounces, kStatRays,
+  kStatSamplesMin, kStatSamplesMax, kStatBouncesMin, kStatBouncesMax, kStatCount
+};
+
+} // namespace rt

@@ -1,0 +1,516 @@
+"""Pins the CPU oracle against the known-answer vectors held by the reference's own Jest
+tests.  Every test cites the reference test it transcribes
+(`/root/reference/tests/...`).  Runs on CPU (`-m "not gpu"`)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from oracle_binding import d3, lib
+from mcp_raytracer_b200 import scenes
+from mcp_raytracer_b200.scene_data import RT_OBJ_PLANE, RT_OBJ_QUAD, RT_OBJ_SPHERE, FlatScene
+
+INF = float("inf")
+
+
+def sphere_hit(c, r, o, d, tmin, tmax):
+    out = (C.c_double * 8)()
+    h = lib().orc_sphere_hit(d3(c), r, d3(o), d3(d), tmin, tmax, out)
+    return list(out) if h else None
+
+
+def planar_hit(kind, q, u, v, o, d, tmin=0.0, tmax=INF):
+    out = (C.c_double * 8)()
+    h = lib().orc_planar_hit(kind, d3(q), d3(u), d3(v), d3(o), d3(d), tmin, tmax, out)
+    return list(out) if h else None
+
+
+def unit(v):
+    out = (C.c_float * 3)()
+    lib().orc_unit(d3(v), out)
+    return list(out)
+
+
+# ---------------------------------------------------------------- Philox (Random123 KAT)
+def test_philox4x32_10_known_answers():
+    def ph(ctr, key):
+        out = (C.c_uint32 * 4)()
+        lib().orc_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        return list(out)
+
+    assert ph([0] * 4, [0] * 2) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert ph([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert ph([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
+        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+# ---------------------------------------------------------------- tests/entities/sphere.test.ts
+def test_sphere_hit_vectors():  # sphere.test.ts:16-90
+    c, r = (0, 0, -1), 0.5
+    h = sphere_hit(c, r, (0, 0, 0), (0, 0, -1), 0, INF)
+    assert h and h[0] == pytest.approx(0.5) and h[3] == pytest.approx(-0.5) and h[7] == 1.0
+    assert (h[4], h[5], h[6]) == pytest.approx((0, 0, 1))
+    assert sphere_hit(c, r, (0, 1, 0), (0, 0, -1), 0, INF) is None
+    h = sphere_hit(c, r, (0, 0, -1), (0, 0, -1), 0.001, INF)  # from inside
+    assert h and h[0] == pytest.approx(0.5) and h[3] == pytest.approx(-1.5) and h[7] == 0.0
+    assert (h[4], h[5], h[6]) == pytest.approx((0, 0, 1))  # flipped inward
+    h = sphere_hit(c, r, (0, 0.5, 0), (0, 0, -1), 0, INF)  # tangent
+    assert h and h[0] == pytest.approx(1.0) and h[2] == pytest.approx(0.5) and h[3] == pytest.approx(-1.0) and h[7] == 1.0
+    assert sphere_hit(c, r, (0, 0, 0), (0, 0, -1), 0.6, 1.0) is None
+    assert sphere_hit(c, r, (0, 0, 0), (0, 0, -1), 0.0, 0.4) is None
+
+
+def test_sphere_pdf_value():  # sphere.test.ts:100-137
+    c, r = (0, 0, -1), 0.5
+    assert lib().orc_sphere_pdf_value(d3(c), r, d3((0, 0, 0)), d3(unit((0, 1, 0)))) == 0
+    v = lib().orc_sphere_pdf_value(d3(c), r, d3((0, 0, 0)), d3(unit((0, 0, -1))))
+    assert v == pytest.approx(1 / (2 * math.pi * (1 - math.sqrt(0.75))), abs=1e-5)
+    far = lib().orc_sphere_pdf_value(d3(c), r, d3((0, 0, 4)), d3(unit((0, 0, -1))))
+    assert far > v  # smaller solid angle, higher pdf (sphere.test.ts:139-160)
+
+
+def test_sphere_pdf_samples_stay_in_cone():  # sphere.test.ts:189-211
+    c, r, o = (0, 0, -1), 0.5, (0, 0, 0)
+    n = 200
+    out = (C.c_float * (3 * n))()
+    lib().orc_sphere_pdf_random(d3(c), r, d3(o), 42, n, out)
+    v = np.array(out, np.float64).reshape(n, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 1, atol=1e-4)
+    cos_max = math.sqrt(1 - r * r / 1.0)
+    assert np.all(v @ np.array([0, 0, -1.0]) >= cos_max - 1e-4)
+    for k in range(n):  # every sampled direction hits the sphere => pdf > 0
+        assert lib().orc_sphere_pdf_value(d3(c), r, d3(o), d3(v[k])) > 0 or (v[k] @ np.array([0, 0, -1.0])) < cos_max + 1e-4
+
+
+# ---------------------------------------------------------------- tests/entities/quad.test.ts
+Q, U, V = (0, 0, 5), (1, 0, 0), (0, 1, 0)
+
+
+def test_quad_hits():  # quad.test.ts:50-118, :136-161, :356-370
+    h = planar_hit(RT_OBJ_QUAD, Q, U, V, (0.5, 0.5, 0), (0, 0, 1))
+    assert h and h[0] == pytest.approx(5) and (h[1], h[2], h[3]) == pytest.approx((0.5, 0.5, 5))
+    assert planar_hit(RT_OBJ_QUAD, Q, U, V, (1.5, 0.5, 0), (0, 0, 1)) is None
+    for corner in [(0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0)]:  # inclusive edges
+        h = planar_hit(RT_OBJ_QUAD, Q, U, V, corner, (0, 0, 1))
+        assert h and h[0] == pytest.approx(5) and h[1] == pytest.approx(corner[0]) and h[2] == pytest.approx(corner[1])
+    assert planar_hit(RT_OBJ_QUAD, Q, U, V, (0.5, 0.5, 0), (1, 0, 0)) is None  # parallel
+    assert planar_hit(RT_OBJ_QUAD, Q, U, V, (1.0001, 0.5, 0), (0, 0, 1)) is None
+    h = planar_hit(RT_OBJ_QUAD, Q, U, V, (0.5, 0.5, 0), (0, 0, 1))  # from -z side
+    assert h[7] == 0.0 and h[6] == pytest.approx(-1)
+    h = planar_hit(RT_OBJ_QUAD, Q, U, V, (0.5, 0.5, 10), (0, 0, -1))  # from +z side
+    assert h[7] == 1.0 and h[6] == pytest.approx(1)
+
+
+def test_quad_bbox_padding():  # quad.test.ts:164-203
+    out = (C.c_double * 6)()
+    lib().orc_object_bbox(RT_OBJ_QUAD, d3(Q), d3(U), d3(V), 0.0, out)
+    b = list(out)
+    assert b[0] == pytest.approx(-1e-4) and b[1] == pytest.approx(-1e-4) and b[2] == pytest.approx(5 - 1e-4)
+    assert b[3] == pytest.approx(1 + 1e-4) and b[4] == pytest.approx(1 + 1e-4) and b[5] == pytest.approx(5 + 1e-4)
+
+
+def test_quad_pdf_value():  # quad.test.ts:225-261
+    d = unit((0.5, 0.5, 5))
+    v = lib().orc_quad_pdf_value(d3(Q), d3(U), d3(V), d3((0, 0, 0)), d3(d))
+    dist2 = 0.5**2 + 0.5**2 + 25
+    cosine = abs(d[2])
+    assert v == pytest.approx(dist2 / (1.0 * cosine), abs=1e-4)
+    assert lib().orc_quad_pdf_value(d3(Q), d3(U), d3(V), d3((0, 0, 0)), d3(unit((5, 5, 1)))) == 0
+
+
+def test_quad_pdf_random_points_at_quad():  # quad.test.ts:264-300
+    n = 100
+    out = (C.c_float * (3 * n))()
+    lib().orc_quad_pdf_random(d3(Q), d3(U), d3(V), d3((0, 0, 0)), 7, n, out)
+    v = np.array(out, np.float64).reshape(n, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 1, atol=1e-4)
+    for k in range(n):
+        assert lib().orc_quad_pdf_value(d3(Q), d3(U), d3(V), d3((0, 0, 0)), d3(v[k])) > 0
+
+
+# ---------------------------------------------------------------- tests/entities/plane.test.ts
+def plane_intersect(q, u, v, o, d, tmin=0.0, tmax=INF):
+    out = (C.c_double * 11)()
+    lib().orc_plane_intersect(d3(q), d3(u), d3(v), d3(o), d3(d), tmin, tmax, out)
+    return list(out)
+
+
+def test_plane_ctor_and_intersect():  # plane.test.ts:17-136
+    r = plane_intersect(Q, U, V, (0, 0, 0), (0, 0, 1))
+    assert r[0:3] == pytest.approx([0, 0, 1]) and r[3] == pytest.approx(5) and r[4:7] == pytest.approx([0, 0, 1])
+    assert r[7] == 1.0 and r[8] == pytest.approx(5) and r[9] == pytest.approx(0) and r[10] == pytest.approx(0)
+    # tilted plane: normal = unit(u x v), d = n.q
+    r = plane_intersect((1, 1, 1), (1, 1, 0), (0, 1, 1), (0, 0, 0), (0, 0, 1))
+    n = np.cross([1, 1, 0], [0, 1, 1]) / np.linalg.norm(np.cross([1, 1, 0], [0, 1, 1]))
+    assert r[0:3] == pytest.approx(list(n), abs=1e-6) and r[3] == pytest.approx(float(n @ [1, 1, 1]), abs=1e-6)
+    assert plane_intersect(Q, U, V, (0, 0, 0), (1, 1, 0))[7] == 0.0  # parallel
+    assert plane_intersect(Q, U, V, (0, 0, 0), (0, 0, 1), 0, 4)[7] == 0.0  # interval ends before plane
+    r = plane_intersect((0, 0, 0), (2, 0, 0), (0, 3, 0), (1, 1.5, -1), (0, 0, 1))
+    assert r[7] == 1.0 and r[8] == pytest.approx(1) and r[9] == pytest.approx(0.5) and r[10] == pytest.approx(0.5)
+
+
+def test_plane_hit_faces():  # plane.test.ts:140-192
+    h = planar_hit(RT_OBJ_PLANE, Q, U, V, (0, 0, 0), (0, 0, 1))
+    assert h and h[0] == pytest.approx(5) and h[6] == pytest.approx(-1) and h[7] == 0.0
+    h = planar_hit(RT_OBJ_PLANE, Q, U, V, (0, 0, 10), (0, 0, -1))
+    assert h and h[0] == pytest.approx(5) and h[6] == pytest.approx(1) and h[7] == 1.0
+    assert planar_hit(RT_OBJ_PLANE, Q, U, V, (0, 0, 0), (1, 0, 0)) is None
+    assert planar_hit(RT_OBJ_PLANE, Q, U, V, (0, 0, 0), unit((0, 1e-6, 1))) is not None  # plane.test.ts:303-317
+    assert planar_hit(RT_OBJ_PLANE, Q, U, V, (0, 0, 10), (0, 0, 1)) is None  # negative t
+
+
+def test_plane_bboxes():  # plane.test.ts:212-286
+    out = (C.c_double * 6)()
+    lib().orc_object_bbox(RT_OBJ_PLANE, d3((0, 0, 5)), d3((1, 0, 0)), d3((0, 1, 0)), 0.0, out)
+    assert out[0] == -INF and out[1] == -INF and out[2] == pytest.approx(5 - 1e-4) and out[3] == INF and out[5] == pytest.approx(5 + 1e-4)
+    lib().orc_object_bbox(RT_OBJ_PLANE, d3((0, 3, 0)), d3((1, 0, 0)), d3((0, 0, 1)), 0.0, out)
+    assert out[0] == -INF and out[1] == pytest.approx(3 - 1e-4) and out[2] == -INF and out[4] == pytest.approx(3 + 1e-4)
+    lib().orc_object_bbox(RT_OBJ_PLANE, d3((-2, 0, 0)), d3((0, 1, 0)), d3((0, 0, 1)), 0.0, out)
+    assert out[0] == pytest.approx(-2 - 1e-4) and out[1] == -INF and out[3] == pytest.approx(-2 + 1e-4) and out[4] == INF
+    lib().orc_object_bbox(RT_OBJ_PLANE, d3((0, 0, 0)), d3((1, 1, 0)), d3((0, 1, 1)), 0.0, out)
+    assert list(out) == [-INF, -INF, -INF, INF, INF, INF]
+
+
+def test_negative_radius_sphere_box_is_inverted():  # SURVEY.md App. A.4 (sphere.ts:25-30)
+    out = (C.c_double * 6)()
+    lib().orc_object_bbox(RT_OBJ_SPHERE, d3((-0.5, 0.25, -0.5)), d3((0, 0, 0)), d3((0, 0, 0)), -0.24, out)
+    assert out[0] > out[3] and out[1] > out[4] and out[2] > out[5]
+
+
+# ---------------------------------------------------------------- tests/geometry/aabb.test.ts
+def test_aabb_vectors():  # aabb.test.ts:8-110
+    mn, mx = d3((-1, -1, -1)), d3((1, 1, 1))
+    assert lib().orc_aabb_hit(mn, mx, d3((0, 0, -5)), d3((0, 0, 1)), 0.1, 100) == 1
+    assert lib().orc_aabb_hit(mn, mx, d3((5, 0, 0)), d3((0, 0, 1)), 0.1, 100) == 0
+    assert lib().orc_aabb_hit(mn, mx, d3((0, 0, -5)), d3((0, 0, 1)), 0.1, 3) == 0
+    out = (C.c_double * 6)()
+    lib().orc_surrounding_box(mn, mx, d3((0, 0, 0)), d3((2, 2, 2)), out)
+    assert list(out) == [-1, -1, -1, 2, 2, 2]
+    lib().orc_surrounding_box(d3((INF,) * 3), d3((-INF,) * 3), mn, mx, out)  # empty is the identity
+    assert list(out) == [-1, -1, -1, 1, 1, 1]
+
+
+# ---------------------------------------------------------------- tests/geometry/bvh.test.ts, hittableList.test.ts
+def _sphere_scene(spheres):
+    return {
+        "camera": {"vfov": 90, "from": [0, 0, 0], "at": [0, 0, -1], "up": [0, 1, 0], "aperture": 0, "focus": 1,
+                   "background": {"type": "gradient", "top": [1, 1, 1], "bottom": [0.5, 0.7, 1.0]}},
+        "materials": [{"id": "m", "material": {"type": "lambert", "color": [0.5, 0.5, 0.5]}}],
+        "objects": [{"type": "sphere", "pos": list(c), "r": r, "material": "m"} for c, r in spheres],
+    }
+
+
+def test_bvh_equals_linear_list():  # bvh.test.ts:52-159
+    four = [((0, 0, -1), 0.5), ((-1, 0, -1), 0.5), ((1, 0, -1), 0.5), ((0, -100.5, -1), 100)]
+    cam = ob.OracleCamera(_sphere_scene(four), {"width": 8, "samples": 1})
+    ids, t, _, _ = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 0.1, 100)
+    assert ids[0] == 0 and t[0] == pytest.approx(0.5)
+    ids, t, _, _ = cam.trace_rays([[0, 5, 0]], [[0, 1, 0]], 0.1, 100)
+    assert ids[0] == -1
+    d = unit((0.5, -0.5, -1))
+    a = cam.trace_rays([[0, 0, 0]], [d], 0.1, 100, use_bvh=True)
+    b = cam.trace_rays([[0, 0, 0]], [d], 0.1, 100, use_bvh=False)
+    assert a[0][0] == b[0][0] and a[1][0] == pytest.approx(b[1][0])
+    ten = [((i - 5, 0, -5), 0.3) for i in range(10)]
+    cam = ob.OracleCamera(_sphere_scene(ten), {"width": 8, "samples": 1})
+    a = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 0.1, 100, use_bvh=True)
+    b = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 0.1, 100, use_bvh=False)
+    assert a[0][0] == b[0][0] == 5 and a[1][0] == pytest.approx(b[1][0]) == pytest.approx(4.7)
+
+
+def test_hittable_list_closest_hit():  # hittableList.test.ts:55-123
+    three = [((0, 0, -1), 0.5), ((0, 0, -2), 0.5), ((0, 0, -3), 0.5)]
+    cam = ob.OracleCamera(_sphere_scene(three), {"width": 8, "samples": 1})
+    for use_bvh in (True, False):
+        ids, t, _, _ = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 0, INF, use_bvh=use_bvh)
+        assert ids[0] == 0 and t[0] == pytest.approx(0.5)
+        ids, t, _, _ = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 1.0, INF, use_bvh=use_bvh)
+        assert t[0] == pytest.approx(1.5)
+        ids, t, _, _ = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 2.0, INF, use_bvh=use_bvh)
+        assert t[0] == pytest.approx(2.5)
+        ids, _, _, _ = cam.trace_rays([[0, 0, 0]], [[0, 0, -1]], 0.6, 0.9, use_bvh=use_bvh)
+        assert ids[0] == -1
+
+
+def test_bvh_matches_brute_force_on_random_rays():
+    """Not a reference vector: cross-check of the BVH restatement against the no-BVH list on
+    every generator scene (SURVEY.md §8c 'cross-check it with an independent brute-force mode')."""
+    rng = np.random.default_rng(3)
+    for sd in (scenes.generateDefaultSceneData(), scenes.generateCornellSceneData(),
+               scenes.generateSpheresSceneData({"count": 60, "seed": 5}), scenes.generateRainSceneData({"count": 300, "seed": 2})):
+        cam = ob.OracleCamera(sd, {"width": 8, "samples": 1})
+        n = 400
+        o = rng.uniform(-1.5, 1.5, (n, 3)).astype(np.float32) + np.array([0, 0.5, 0.5], np.float32)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        a = cam.trace_rays(o, d, use_bvh=True)
+        b = cam.trace_rays(o, d, use_bvh=False)
+        # the negative-radius sphere of the default scene is only reachable without the BVH
+        # (inverted box): exclude rays whose list hit is that object
+        neg = [i for i, ob_ in enumerate(sd["objects"]) if ob_.get("r", 1) < 0]
+        keep = ~np.isin(b[0], neg)
+        same_t = np.isclose(a[1][keep], b[1][keep], rtol=1e-12, atol=0) | (np.isinf(a[1][keep]) & np.isinf(b[1][keep]))
+        assert same_t.all()
+
+
+# ---------------------------------------------------------------- tests/geometry/pdf.test.ts, onbasis.test.ts
+def test_cosine_pdf_values():  # pdf.test.ts:55-77
+    n = (0, 1, 0)
+    f = lib().orc_cosine_pdf_value
+    assert f(d3(n), d3((0, 1, 0))) == pytest.approx(1 / math.pi)
+    assert f(d3(n), d3(unit((1, 1, 0)))) == pytest.approx(0.7071 / math.pi, abs=1e-4)
+    assert f(d3(n), d3((1, 0, 0))) == pytest.approx(0)
+    assert f(d3(n), d3((0, -1, 0))) == 0
+
+
+def test_cosine_generate_statistics():  # pdf.test.ts:28-52, :159-179
+    cnt = 4000
+    out = (C.c_float * (3 * cnt))()
+    lib().orc_cosine_pdf_generate(d3((0, 1, 0)), 11, cnt, out)
+    v = np.array(out, np.float64).reshape(cnt, 3)
+    assert np.allclose(np.linalg.norm(v, axis=1), 1, atol=1e-3)
+    assert np.all(v[:, 1] >= -1e-6)
+    lib().orc_random_cosine_direction(12, cnt, out)
+    z = np.array(out, np.float64).reshape(cnt, 3)[:, 2]
+    assert z.mean() == pytest.approx(2 / 3, abs=0.02)
+
+
+def test_mixture_pdf_value_and_selection():  # pdf.test.ts:80-156
+    mv = lib().orc_mixture_value
+    arr = lambda a: (C.c_double * len(a))(*a)  # noqa: E731
+    assert mv(2, arr([1.0, 1.0]), arr([0.5, 0.5])) == pytest.approx(1.0)
+    assert mv(2, arr([1.0, 3.0]), arr([0.5, 0.5])) == pytest.approx(2.0)
+    assert mv(2, arr([1.0, 3.0]), arr([1.0, 3.0])) == pytest.approx(2.5)
+    rng = np.random.default_rng(0)
+    picks = [lib().orc_mixture_select(2, arr([1.0, 3.0]), float(u)) for u in rng.random(4000)]
+    assert np.mean(np.array(picks) == 0) == pytest.approx(0.25, abs=0.03)  # 1:3 ratio (pdf.test.ts:94-124)
+
+
+def test_onb_orthonormal():  # onbasis.test.ts
+    for n in [(0, 1, 0), (1, 0, 0), (0.95, 0.1, 0.2), (1, 2, 3), (0, 0, -4)]:
+        out = (C.c_float * 9)()
+        lib().orc_onb(d3(n), out)
+        b = np.array(out, np.float64).reshape(3, 3)
+        assert np.allclose(b @ b.T, np.eye(3), atol=1e-5)
+        assert np.allclose(b[2], np.array(n) / np.linalg.norm(n), atol=1e-6)
+
+
+# ---------------------------------------------------------------- tests/materials/*.test.ts
+def _mat_scene(material):
+    return FlatScene({"camera": {}, "materials": [{"id": "m", "material": material}],
+                      "objects": [{"type": "sphere", "pos": [0, 0, 0], "r": 1, "material": "m"}]})
+
+
+def scatter(material, rd, n=(0, 1, 0), front=True, seed=1, sample=0, p=(0, 0, 0)):
+    fs = _mat_scene(material)
+    out = (C.c_double * 9)()
+    em = (C.c_float * 3)()
+    rc = lib().orc_material_scatter(C.byref(fs.desc), int(fs.obj_material[0]), d3((0, 1, 0)), d3(rd), d3(p), d3(n),
+                                    1 if front else 0, seed, sample, out, em)
+    assert rc >= 0
+    return (list(out) if rc == 1 else None), list(em)
+
+
+def test_metal_reflection_and_fuzz():  # metal.test.ts:12-74, :127-175
+    r, _ = scatter({"type": "metal", "color": [0.8, 0.8, 0.8], "fuzz": 0.0}, (1, -1, 0))
+    assert r[0] == 1.0 and r[2:5] == pytest.approx([0.8, 0.8, 0.8])
+    assert r[5:8] == pytest.approx([1 / math.sqrt(2), 1 / math.sqrt(2), 0], abs=1e-5)
+    assert lib().orc_metal_fuzz_clamp(-0.5) == 0 and lib().orc_metal_fuzz_clamp(1.5) == 1 and lib().orc_metal_fuzz_clamp(0.3) == 0.3
+    out = (C.c_float * 3)()
+    lib().orc_reflect(d3((1, -1, 0)), d3((0, 1, 0)), out)
+    assert list(out) == pytest.approx([1, 1, 0])
+    # grazing ray + full fuzz is absorbed sometimes (reflection pushed below the surface)
+    res = [scatter({"type": "metal", "color": [1, 1, 1], "fuzz": 1.0}, (1, -0.01, 0), seed=s)[0] for s in range(200)]
+    assert any(x is None for x in res) and any(x is not None for x in res)
+
+
+def test_dielectric_vectors():  # dielectric.test.ts:30-134
+    r, _ = scatter({"type": "glass", "ior": 1.5}, (0, -1, 0))
+    assert r[0] == 1.0 and r[2:5] == [1, 1, 1]
+    f = lib().orc_dielectric_reflectance
+    assert f(1.0, 1 / 1.5) == pytest.approx(0.04, abs=1e-3)
+    assert f(0.1, 1 / 1.5) > 0.5
+    # total internal reflection: from inside at a grazing angle the ray must reflect
+    d = unit((1, -0.1, 0))
+    for s in range(20):
+        r, _ = scatter({"type": "glass", "ior": 1.5}, d, front=False, seed=s)
+        assert r[8] == 1.0 and r[6] > 0
+
+
+def test_lambertian_and_light():  # lambertian.test.ts, diffuseLight.test.ts, defaultMaterial.test.ts
+    r, em = scatter({"type": "lambert", "color": [0.1, 0.2, 0.3]}, (0, -1, 0))
+    assert r[0] == 0.0 and r[1] == 1.0 and r[2:5] == pytest.approx([0.1, 0.2, 0.3]) and em == [0, 0, 0]
+    r, em = scatter({"type": "light", "emit": [15, 14, 13]}, (0, -1, 0))
+    assert r is None and em == [15, 14, 13]
+
+
+def test_mixed_material():  # mixedMaterial.test.ts:49-128, :214-240
+    assert lib().orc_mixed_weight_clamp(1.5) == 1 and lib().orc_mixed_weight_clamp(-1) == 0 and lib().orc_mixed_weight_clamp(0.3) == 0.3
+    lam = {"type": "lambert", "color": [0.5, 0.5, 0.5]}
+    met = {"type": "metal", "color": [0.9, 0.9, 0.9], "fuzz": 0.0}
+    for s in range(20):
+        assert scatter({"type": "mixed", "diff": lam, "spec": met, "weight": 1.0}, (1, -1, 0), seed=s)[0][1] == 1.0
+        assert scatter({"type": "mixed", "diff": lam, "spec": met, "weight": 0.0}, (1, -1, 0), seed=s)[0][0] == 1.0
+    picks = [scatter({"type": "mixed", "diff": lam, "spec": met, "weight": 0.3}, (1, -1, 0), seed=s)[0][1] for s in range(2000)]
+    assert np.mean(picks) == pytest.approx(0.3, abs=0.05)
+    _, em = scatter({"type": "mixed", "diff": {"type": "light", "emit": [1, 2, 3]}, "spec": {"type": "light", "emit": [4, 5, 6]}, "weight": 0.3}, (0, -1, 0))
+    assert em == pytest.approx([0.3 * 1 + 0.7 * 4, 0.3 * 2 + 0.7 * 5, 0.3 * 3 + 0.7 * 6], abs=1e-5)
+
+
+def test_layered_material():  # layeredMaterial.test.ts:57-123, :188-200
+    glass = {"type": "glass", "ior": 1.5}
+    paint = {"type": "layered", "outer": glass, "inner": {"type": "lambert", "color": [0.7, 0.3, 0.3]}}
+    kinds = set()
+    for s in range(300):
+        r, _ = scatter(paint, unit((1, -0.3, 0)), seed=s)
+        if r[0] == 1.0:  # reflected off the coat: white attenuation + a ray
+            assert r[2:5] == [1, 1, 1] and r[8] == 1.0
+            kinds.add("reflect")
+        else:            # refracted: the inner Lambertian's pdf result
+            assert r[1] == 1.0 and r[2:5] == pytest.approx([0.7, 0.3, 0.3])
+            kinds.add("inner")
+    assert kinds == {"reflect", "inner"}
+    coated = {"type": "layered", "outer": glass, "inner": {"type": "metal", "color": [0.8, 0.8, 0.8], "fuzz": 0.0}}
+    got_inner = False
+    for s in range(100):
+        r, _ = scatter(coated, (0, -1, 0), seed=s)
+        if r is not None and r[8] == 0.0:
+            assert r[0] == 1.0 and r[2:5] == pytest.approx([0.8, 0.8, 0.8])
+            got_inner = True
+    assert got_inner
+    _, em = scatter({"type": "layered", "outer": glass, "inner": {"type": "light", "emit": [2, 3, 4]}}, (0, -1, 0))
+    assert em == [2, 3, 4]
+
+
+# ---------------------------------------------------------------- tests/camera.test.ts
+def _empty_world(camera=None):
+    sd = _sphere_scene([((0, 0, 1e6), 1e-3)])  # nothing any test ray can reach ("emptyWorld")
+    if camera:
+        sd["camera"].update(camera)
+    return sd
+
+
+def test_camera_dimensions():  # camera.test.ts:161-167, :820-880
+    assert (lambda c: (c.imageWidth, c.imageHeight))(ob.OracleCamera(_empty_world(), {})) == (400, 225)
+    for aspect, h in ((1.0, 400), (16 / 9, 225), (4 / 3, 300)):
+        c = ob.OracleCamera(_empty_world(), {"width": 400, "aspect": aspect})
+        assert (c.imageWidth, c.imageHeight) == (400, h)
+
+
+def test_camera_rays_identical_without_jitter():  # camera.test.ts:202-222
+    c = ob.OracleCamera(_empty_world(), {"width": 20, "samples": 1})
+    o1, d1 = c.get_ray(3, 4, sample=0)
+    o2, d2 = c.get_ray(3, 4, sample=5)
+    assert np.array_equal(o1, o2) and np.array_equal(d1, d2)
+    c = ob.OracleCamera(_empty_world(), {"width": 20, "samples": 4})
+    _, d1 = c.get_ray(3, 4, sample=0)
+    _, d2 = c.get_ray(3, 4, sample=1)
+    assert not np.array_equal(d1, d2)
+
+
+def test_camera_defocus_offsets_origin():  # camera.test.ts:225-330
+    c = ob.OracleCamera(_empty_world({"aperture": 2.0, "focus": 10.0}), {"width": 20, "samples": 4})
+    origins = np.array([c.get_ray(5, 5, sample=s)[0] for s in range(50)])
+    assert np.any(np.abs(origins) > 1e-3)
+    assert np.all(np.linalg.norm(origins, axis=1) <= 1.0 + 1e-5)  # inside the aperture/2 disk
+    c0 = ob.OracleCamera(_empty_world({"aperture": 0.0}), {"width": 20, "samples": 4})
+    assert np.array_equal(c0.get_ray(5, 5, sample=3)[0], np.zeros(3, np.float32))
+
+
+def test_background_gradient():  # camera.test.ts:725-817
+    c = ob.OracleCamera(_empty_world(), {})
+    up, _ = c.ray_color((0, 0, 0), (0, 1, 0))
+    down, _ = c.ray_color((0, 0, 0), (0, -1, 0))
+    assert down[0] == pytest.approx(1.0, abs=0.05) and up[0] == pytest.approx(0.5, abs=0.05) and down.sum() > up.sum()
+    c = ob.OracleCamera(_empty_world({"background": {"type": "gradient", "top": [1, 0, 0], "bottom": [0, 1, 0]}}), {})
+    up, _ = c.ray_color((0, 0, 0), (0, 1, 0))
+    down, _ = c.ray_color((0, 0, 0), (0, -1, 0))
+    assert up[1] > up[0] and down[0] > down[1]
+    c = ob.OracleCamera(_empty_world({"background": {"type": "gradient", "top": [0.5, 0, 0.5], "bottom": [0.5, 0, 0.5]}}), {})
+    for d in ((0, 1, 0), (0, -1, 0)):
+        col, _ = c.ray_color((0, 0, 0), d)
+        assert list(col) == pytest.approx([0.5, 0, 0.5], abs=1e-5)
+
+
+def test_render_stats_counts():  # camera.test.ts:332-357, :381-396
+    r = ob.OracleCamera(_empty_world(), {"width": 10, "aspect": 1.0, "samples": 1}).render()
+    st = r["stats"]
+    assert (st.pixels, st.samples_total, st.samples_min, st.samples_max) == (100, 100, 1, 1)
+    c = ob.OracleCamera(_empty_world(), {"width": 20, "aspect": 1.0, "samples": 1})
+    st = c.render(region=ob.rt_region(5, 5, 10, 10))["stats"]
+    assert st.pixels == 100
+    st = c.render(region=ob.rt_region(15, 15, 10, 10))["stats"]  # clipped at the image edge (camera.ts:390-391)
+    assert st.pixels == 25
+
+
+def test_russian_roulette_bounds_bounces():  # camera.test.ts:591-655
+    sd = scenes.generateCornellSceneData()
+    a = ob.OracleCamera(sd, {"width": 24, "samples": 8, "aTolerance": 0, "roulette": True}).render(threads=4)["stats"]
+    b = ob.OracleCamera(sd, {"width": 24, "samples": 8, "aTolerance": 0, "roulette": False, "depth": 30}).render(threads=4)["stats"]
+    assert a.bounces_total < b.bounces_total
+    assert b.bounces_max <= 30
+
+
+# ---------------------------------------------------------------- tests/scenes/*.test.ts
+def test_scene_generators_structure():
+    c = scenes.generateCornellSceneData()  # scenes.cornell.test.ts:6-24
+    assert len(c["objects"]) == 8 and sum(1 for o in c["objects"] if o.get("light")) == 1 and c["render"]["aspect"] == 1.0
+    assert len(scenes.generateCornellSceneData({"variant": "empty"})["objects"]) == 6
+    assert len(scenes.generateRainSceneData({"count": 20, "seed": 1})["objects"]) == 21  # scenes.rain.test.ts:8-13
+    for n in (5, 50, 200):  # scenes.spheres.test.ts:8-63
+        assert len(scenes.generateSpheresSceneData({"count": n, "seed": 9})["objects"]) == n
+    r10 = scenes.generateSpheresSceneData({"count": 10, "seed": 1})["objects"][0]["r"]
+    r1000 = scenes.generateSpheresSceneData({"count": 1000, "seed": 1})["objects"][0]["r"]
+    assert r1000 < r10
+    d = scenes.generateDefaultSceneData()  # scenes.default.test.ts
+    assert len(d["objects"]) == 10 and sum(1 for o in d["objects"] if o.get("light")) == 2
+    a = scenes.generateSpheresSceneData({"count": 30, "seed": 77})
+    b = scenes.generateSpheresSceneData({"count": 30, "seed": 77})
+    assert a == b  # deterministic for a seed
+
+
+def test_seeded_random_batch_equals_scalar():
+    a = scenes.SeededRandom(12345)
+    b = scenes.SeededRandom(12345)
+    xs = [a.next() for _ in range(1000)]
+    ys = b.next_batch(1000)
+    assert np.array_equal(np.array(xs), ys)
+    assert a.next() == b.next()
+    assert all(0 <= x < 1 for x in xs)
+
+
+def test_mulberry32_known_values():
+    """mulberry32(seed=1) first outputs, computed independently with exact uint32 arithmetic."""
+    def mb(seed, n):
+        out, s = [], seed
+        for _ in range(n):
+            s = (s + 0x6D2B79F5) & 0xFFFFFFFF
+            t = s
+            t = ((t ^ (t >> 15)) * (t | 1)) & 0xFFFFFFFF
+            t ^= (t + (((t ^ (t >> 7)) * (t | 61)) & 0xFFFFFFFF)) & 0xFFFFFFFF
+            out.append(((t ^ (t >> 14)) & 0xFFFFFFFF) / 4294967296)
+        return out
+    r = scenes.SeededRandom(1)
+    assert [r.next() for _ in range(8)] == mb(1, 8)
+
+
+# ---------------------------------------------------------------- output quantisation / adaptive rule
+def test_write_color_quantisation():  # camera.ts:455-472 (asserted by no reference test: oracle-pinned)
+    out = (C.c_uint8 * 3)()
+    lib().orc_write_color(d3((0.0, 0.25, 1.0)), out)
+    assert list(out) == [0, 127, 255]
+    lib().orc_write_color(d3((4.0, float("nan"), -1.0)), out)
+    assert list(out) == [255, 0, 0]
+
+
+def test_pixel_converged_rule():  # camera.ts:348-368
+    c = ob.OracleCamera(_empty_world(), {"samples": 100, "aTolerance": 0.05, "aBatch": 10})
+    pc = lib().orc_pixel_converged
+    assert pc(c.h, 1, 1.0, 1.0) == 0            # < 2 samples
+    assert pc(c.h, 7, 7.0, 7.0) == 0            # not on a batch boundary
+    assert pc(c.h, 10, 10.0, 10.0) == 1         # zero variance => converged
+    # mean 1, sample variance 1 at n=10: CI = 1.96/sqrt(10) = 0.62 > 0.05
+    assert pc(c.h, 10, 10.0, 19.0) == 0
+    c0 = ob.OracleCamera(_empty_world(), {"samples": 100, "aTolerance": 0.0})
+    assert pc(c0.h, 10, 10.0, 10.0) == 0        # adaptive off
