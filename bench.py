@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the path-tracing hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload C2]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full render of the workload (default BASELINE.json configs[1]: Cornell box
+1024x1024 @ 1024 spp, emissive quad light + mixture-PDF light sampling, adaptive sampling off).
+Rank 0 prints ONE JSON line (contract in the task statement):
+
+  value     Mpaths/s, whole job, scene resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e       same metric through the public API with HOST buffers: SceneData flatten + BVH build +
+            H2D upload + render + framebuffer gather + D2H, wall clock, every step
+  roofline  FP32-pipe roofline of the render kernel: algorithmic flops (SURVEY.md §8d model, event
+            counts from the CPU oracle on a bounded sample) / CUDA-event time, against the FP32 FMA
+            peak measured in this run (MEASURED_PEAKS.json has no FP32 figure); HBM traffic beside it
+  cpu_baseline  the C++ restatement of the reference (oracle/, kind "port": the TypeScript reference
+            cannot run here) on the box's host cores, parallelised like the reference's worker
+            threads (row strips, nproc-1 threads), on a bounded sample
+
+`--impl reference` times that CPU port alone, on the same workload/metric (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs (SURVEY.md §8d for the concrete inputs)
+    "C1": ("spheres-scene 400x225 @16spp depth 10 (BASELINE configs[0])", "spheres", {"count": 100, "seed": 12345},
+           {"width": 400, "samples": 16, "depth": 10, "aTolerance": 0}),
+    "C2": ("cornell-scene 1024x1024 @1024spp, quad light + PDF light sampling (BASELINE configs[1])", "cornell", {},
+           {"width": 1024, "samples": 1024, "aTolerance": 0}),
+    "C3": ("weekend-final ~480 spheres 1920x1080 @512spp (BASELINE configs[2])", "weekend", {"seed": 1},
+           {"width": 1920, "samples": 512, "aTolerance": 0}),
+    "C4": ("rain-scene 100k spheres 3840x2160 @64spp (BASELINE configs[3])", "rain", {"count": 100000, "seed": 1, "sphereRadius": 0.01},
+           {"width": 3840, "samples": 64, "aTolerance": 0}),
+    "C5": ("layered/mixed-material scene 2048x2048 @256spp (BASELINE configs[4])", "layered", {},
+           {"width": 2048, "samples": 256, "aTolerance": 0}),
+}
+
+
+def make_scene(kind, options):
+    from mcp_raytracer_b200 import scenes
+
+    return {
+        "spheres": scenes.generateSpheresSceneData, "cornell": scenes.generateCornellSceneData,
+        "weekend": scenes.generateWeekendFinalSceneData, "rain": scenes.generateRainSceneData,
+        "layered": scenes.generateLayeredMixedSceneData,
+    }[kind](options)
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work model — SURVEY.md §8(d): flops the REFERENCE algorithm spends, with event
+# counts taken from the oracle walking the reference's own BVH topology.
+# ------------------------------------------------------------------------------------------
+def algorithmic_flops(cnt, n_lights, aperture):
+    ray = (21 * cnt["box_tests"] + 23 * cnt["sphere_miss"] + 52 * cnt["sphere_hit"] + 16 * cnt["planar_treject"]
+           + 57 * cnt["quad_outside"] + 72 * cnt["quad_hit"] + 28 * cnt["plane_hit"])
+    lambert = 110 if n_lights == 0 else 200 + 90 * (n_lights - 1)
+    path = ((31 + (25 if aperture > 0 else 0)) * cnt["paths"] + 8 * cnt["rr"] + 24 * cnt["background"] + lambert * cnt["lambert"]
+            + 62 * cnt["metal"] + 35 * cnt["metal_fuzz0"] + 60 * cnt["dielectric"] + 6 * cnt["hits"])
+    return ray + path
+
+
+def cpu_reference_run(sd, opts, target_seconds, threads):
+    """Times the oracle on a bounded sample: the full image at a reduced spp chosen from a 1-spp
+    calibration so the run lasts about `target_seconds` (adaptive sampling is off, so cost is
+    linear in spp)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleCamera
+
+    base = dict(opts)
+    cal = dict(base, samples=2)
+    cam = OracleCamera(sd, cal)
+    t0 = time.perf_counter()
+    r = cam.render(threads=threads, want_counters=False)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    per_spp = dt / 2
+    spp = int(max(2, min(base["samples"], target_seconds / per_spp)))
+    cam = OracleCamera(sd, dict(base, samples=spp))
+    t0 = time.perf_counter()
+    r = cam.render(threads=threads, want_counters=True)
+    dt = time.perf_counter() - t0
+    st = r["stats"]
+    return {
+        "seconds": dt, "spp": spp, "paths": int(st.samples_total), "rays": int(st.rays), "counters": r["counters"],
+        "n_lights": cam.n_lights, "width": cam.imageWidth, "height": cam.imageHeight,
+        "mpaths_per_s": st.samples_total / dt / 1e6, "grays_per_s": st.rays / dt / 1e9,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=None, help="override spp (development only; the default is the BASELINE config)")
+    ap.add_argument("--width", type=int, default=None, help="override width (development only)")
+    ap.add_argument("--bvh", default="auto")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    label, kind, scene_opts, ropts = WORKLOADS[args.workload]
+    ropts = dict(ropts)
+    overridden = False
+    if args.samples:
+        ropts["samples"] = args.samples; overridden = True
+    if args.width:
+        ropts["width"] = args.width; overridden = True
+    ropts["bvh"] = args.bvh
+    cpu_threads = max(1, (os.cpu_count() or 2) - 1)  # os.cpus().length - 1, src/raytracer.ts:61
+
+    # ---------------------------------------------------------------- reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sd = make_scene(kind, scene_opts)
+        vals, last = [], None
+        for i in range(args.warmup + args.steps):
+            last = cpu_reference_run(sd, ropts, target_seconds=max(2.0, min(args.cpu_seconds, 60.0 / max(1, args.warmup + args.steps))), threads=cpu_threads)
+            if i >= args.warmup:
+                vals.append(last)
+        v = sum(x["paths"] for x in vals) / sum(x["seconds"] for x in vals) / 1e6
+        sample = f"{last['width']}x{last['height']} full image @{last['spp']}spp of {ropts['samples']} (adaptive off: cost linear in spp)"
+        line = {
+            "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * sum(x["seconds"] for x in vals) / len(vals), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32-store/f64-scalar", "data": "synthetic",
+            "config": {"workload": label, "sample": sample},
+            "grays_per_s": sum(x["rays"] for x in vals) / sum(x["seconds"] for x in vals) / 1e9,
+            "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of the TypeScript reference (no node toolchain in the image); row strips, one per thread, like src/raytracer.ts:60-90"},
+            "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- B200 arm
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mcp_raytracer_b200 import _native, createCameraFromSceneData, measureFp32Peak
+    from mcp_raytracer_b200.distributed import gather_framebuffer, merge_stats
+    from mcp_raytracer_b200.scene_data import rt_stats
+
+    if not torch.cuda.is_available() or _native.lib().rt_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sd = make_scene(kind, scene_opts)
+    part = {"partIndex": rank, "partCount": world, "device": local_rank}
+    cam = createCameraFromSceneData(sd, {**ropts, **part})
+    W, H = cam.imageWidth, cam.imageHeight
+    stream = torch.cuda.current_stream()
+    cam.setStream(stream.cuda_stream)
+    fb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    stats_dev = torch.zeros(64, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    host_fb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+
+    def read_stats():
+        import ctypes
+
+        raw = bytes(stats_dev.cpu().numpy())
+        assert ctypes.sizeof(rt_stats) == 64 == len(raw)
+        return rt_stats.from_buffer_copy(raw)
+
+    def step_device():
+        cam.renderRegionDevice(None, fb.data_ptr(), 0, 0, stats_dev.data_ptr())
+
+    # warm-up (untimed)
+    for _ in range(max(args.warmup, 3) if args.warmup >= 3 else args.warmup):
+        step_device()
+    barrier()
+    fp32_peak, sm_attr_mhz = measureFp32Peak(local_rank) if rank == 0 else (None, None)
+    barrier()
+
+    # ---- timed region: EXACTLY K steps, CUDA events per step, L2 flushed between steps ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()
+        ev[k][0].record(stream)
+        step_device()
+        ev[k][1].record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    local_ms = sum(step_ms)
+    st_local = read_stats()
+    t = torch.tensor([local_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([st_local.pixels, st_local.samples_total, st_local.bounces_total, st_local.rays], dtype=torch.int64, device=dev)
+    mins = torch.tensor([st_local.samples_min, st_local.bounces_min], dtype=torch.int64, device=dev)
+    maxs = torch.tensor([st_local.samples_max, st_local.bounces_max], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    merge_stats(sums, mins, maxs)
+    total_ms = float(t.item())
+    paths_per_step, rays_per_step = int(sums[1].item()), int(sums[3].item())
+    kernel_launches_per_step = int(st_local.kernel_launches)
+
+    # ---- end-to-end through the public API, host buffers, every step: flatten + build + H2D +
+    #      render + gather + D2H ----
+    from mcp_raytracer_b200.scene_data import FlatScene
+
+    def e2e_step():
+        c = createCameraFromSceneData(sd, {**ropts, **part})
+        c.setStream(stream.cuda_stream)
+        if world > 1:
+            fb.zero_()
+            c.renderRegionDevice(None, fb.data_ptr(), 0, 0, stats_dev.data_ptr())
+            gather_framebuffer(fb)
+            if rank == 0:
+                host_fb.copy_(fb, non_blocking=True)
+            torch.cuda.synchronize()
+        else:
+            c.render(host_fb.numpy().reshape(-1))
+        c.close()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    fs = FlatScene(sd)
+    h2d = int(sum(a.nbytes for a in (fs.obj_type, fs.obj_pos, fs.obj_u, fs.obj_v, fs.obj_r, fs.obj_material, fs.obj_light,
+                                     fs.mat_type_a, fs.mat_color_a, fs.mat_param_a, fs.mat_child_a)))
+    d2h = W * H * 3 + 64
+
+    if rank != 0:
+        cam.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
+    grays = rays_per_step * args.steps / (total_ms * 1e-3) / 1e9
+    e2e_value = paths_per_step * args.steps / e2e_s / 1e6
+
+    # ---- CPU baseline + algorithmic-work model (oracle = checker / baseline only) ----
+    cpu, roof = None, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    if not args.no_cpu_baseline:
+        c = cpu_reference_run(sd, ropts, target_seconds=args.cpu_seconds, threads=cpu_threads)
+        sample = f"{c['width']}x{c['height']} full image @{c['spp']}spp of {ropts['samples']} (adaptive off: cost linear in spp)"
+        cpu = {"value": c["mpaths_per_s"], "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
+               "grays_per_s": c["grays_per_s"], "seconds": c["seconds"],
+               "note": "C++ restatement of the TypeScript reference (cannot run here); row strips, one per thread, like src/raytracer.ts:60-90"}
+        flops_per_path = algorithmic_flops(c["counters"], c["n_lights"], float(sd["camera"].get("aperture", 0))) / max(1, c["counters"]["paths"])
+        kernel_s = (total_ms * 1e-3) / args.steps  # one render kernel per step (max over ranks)
+        achieved = flops_per_path * paths_per_step / kernel_s / 1e12
+        peak = fp32_peak * world
+        hbm_bytes = W * H * 3 + h2d  # compulsory traffic: scene once + RGB8 out
+        roof = {
+            "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": f"FP32 FFMA microbenchmark in this run (rt_measure_fp32_peak): {fp32_peak:.1f} TFLOP/s per GPU at <= {sm_attr_mhz:.0f} MHz; "
+                           "MEASURED_PEAKS.json holds HBM/bf16 peaks only",
+            "flops_per_path": flops_per_path, "flops_model": "SURVEY.md §8d, event counts from the oracle walking the reference BVH",
+            "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / kernel_s / 1e9,
+                    "peak_gbs": peaks.get("hbm_gbs"), "note": "scene is register/L1-resident; HBM is not the bound"},
+        }
+
+    line = {
+        "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": label + (" [OVERRIDDEN size: development run]" if overridden else ""), "image": f"{W}x{H}", "spp": ropts["samples"],
+                   "bvh": {1: "reference", 2: "sah", 3: "list"}.get(cam.info.bvh_kind), "integrator": "megakernel",
+                   "partition": f"16x16 tiles, owner=(tx+ty)%{world}", "rng": "Philox4x32-10 keyed (pixel,sample), counter (block,bounce)",
+                   "l2": "256 MiB memset between steps, outside the per-step CUDA-event pairs"},
+        "grays_per_s": grays, "paths_per_step": paths_per_step, "rays_per_step": rays_per_step,
+        "wall_s_timed_region": wall, "step_ms": step_ms,
+        "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
+        "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "includes": "SceneData flatten + BVH build + H2D + render + gather + D2H of the RGB8 framebuffer and stats"},
+        "gpu_launches": kernel_launches_per_step * args.steps * world,
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    cam.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

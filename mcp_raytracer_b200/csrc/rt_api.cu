@@ -166,7 +166,7 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   } while (0)
   UP(c->hs.nodes, &nodes);
   d.nodes = reinterpret_cast<const F4*>(nodes);
-  UP(c->hs.p0, &d.p0); UP(c->hs.p1, &d.p1); UP(c->hs.p2, &d.p2);
+  UP(c->hs.p0, &d.p0); UP(c->hs.p1, &d.p1); UP(c->hs.p2, &d.p2); UP(c->hs.p3, &d.p3);
   UP(c->hs.slot_info, &d.slot_info); UP(c->hs.exact, &d.exact);
   UP(c->hs.matA, &d.matA); UP(c->hs.matB, &d.matB); UP(c->hs.matE, &d.matE);
   UP(c->hs.lights, &d.lights);

@@ -89,7 +89,7 @@ struct Prim {
   Box ref_box; // exactly the reference's boundingBox()
   Box sah_box; // finite and non-inverted where possible
   bool bounded = true;
-  F4 rec0{}, rec1{}, rec2{};
+  F4 rec0{}, rec1{}, rec2{}, rec3{};
 };
 
 void make_sphere(Prim& p) {
@@ -152,6 +152,9 @@ void make_planar(Prim& p) {
   p.rec0 = F4{(float)nn[0], (float)nn[1], (float)nn[2], (float)p.D};
   p.rec1 = F4{(float)A[0], (float)A[1], (float)A[2], (float)a0};
   p.rec2 = F4{(float)B[0], (float)B[1], (float)B[2], (float)b0};
+  const double eps4 = 4.0 / 16777216.0; // 4 * 2^-24
+  p.rec3 = F4{(float)(std::fabs(A[0]) + std::fabs(A[1]) + std::fabs(A[2])), (float)(std::fabs(B[0]) + std::fabs(B[1]) + std::fabs(B[2])),
+              (float)(eps4 * std::fabs(a0)), (float)(eps4 * std::fabs(b0))};
 }
 
 // ---- build tree (shared by both builders) ----
@@ -303,17 +306,29 @@ struct Flattener {
   const std::vector<Prim>& P;
   const std::vector<BNode>& pool;
   HostScene& S;
+  const std::vector<int>& rank; // per object: position in the reference's visiting order
   int max_depth = 0;
+  bool has_inverted(int bi) const { // does the subtree hold a primitive whose reference box is inverted?
+    const BNode& n = pool[bi];
+    if (n.leaf) {
+      for (int pi : n.prims)
+        for (int a = 0; a < 3; ++a)
+          if (P[pi].ref_box.mn[a] > P[pi].ref_box.mx[a]) return true;
+      return false;
+    }
+    return has_inverted(n.left) || has_inverted(n.right);
+  }
   void push_slot(int pi) {
     const Prim& p = P[pi];
     S.p0.push_back(p.rec0);
     S.p1.push_back(p.rec1);
     S.p2.push_back(p.rec2);
+    S.p3.push_back(p.rec3);
     S.slot_info.push_back(I2{p.mat, p.obj | (p.type << 30)});
     ExactPrim e;
     std::memset(&e, 0, sizeof(e));
     put3(e.q, p.q); put3(e.u, p.u); put3(e.v, p.v); put3(e.n, p.n); put3(e.w, p.w);
-    e.type = p.type; e.D = p.D; e.r = p.r; e.area = p.area;
+    e.type = p.type; e.rank = rank[pi]; e.D = p.D; e.r = p.r; e.area = p.area;
     S.exact.push_back(e);
   }
   int leaf_ref(const BNode& n) {
@@ -341,6 +356,7 @@ struct Flattener {
     Box rb = r >= 0 ? pool[r].box : empty_box();
     std::memcpy(nd.lmin, lb.mn, 12); std::memcpy(nd.lmax, lb.mx, 12);
     std::memcpy(nd.rmin, rb.mn, 12); std::memcpy(nd.rmax, rb.mx, 12);
+    nd.flags = ((l >= 0 && has_inverted(l)) ? 1 : 0) | ((r >= 0 && has_inverted(r)) ? 2 : 0);
     nd.left = l >= 0 ? emit(l, depth + 1) : kEmptyRef;
     nd.right = r >= 0 ? emit(r, depth + 1) : kEmptyRef;
     S.nodes[idx] = nd;
@@ -435,7 +451,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     if (p.type != OBJ_SPHERE && p.type != OBJ_QUAD) continue;
     DevLight L;
     std::memset(&L, 0, sizeof(L));
-    L.p0 = p.rec0; L.p1 = p.rec1; L.p2 = p.rec2;
+    L.p0 = p.rec0; L.p1 = p.rec1; L.p2 = p.rec2; L.p3 = p.rec3;
     put3(L.q, p.q); put3(L.u, p.u); put3(L.v, p.v);
     L.area = (float)p.area;
     L.radius = (float)p.r;
@@ -455,33 +471,40 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   S.bvh_kind = kind;
   S.n_unbounded = 0;
   std::vector<BNode> pool;
-  Flattener fl{P, pool, S};
-  if (kind == BVH_LIST) {
-    // Same visiting order as the reference's tree (left-to-right over its leaves) so that
-    // exact-t ties resolve to the same primitive; only the box tests are dropped, which
-    // cannot change a nearest hit when no box is inverted.
-    pool.reserve(n);
+  // Visiting order of the reference's own tree: decides which primitive keeps a hit when two
+  // distances are exactly equal (first visited wins, hittableList.ts:76-84 / bvh.ts:139-145).
+  // Ties need coincident surfaces, so large procedural scenes skip the O(n log^2 n) build.
+  std::vector<int> rank(n);
+  std::iota(rank.begin(), rank.end(), 0);
+  std::vector<BNode> ref_pool;
+  int ref_root = -1;
+  if (kind != BVH_SAH || n <= 4096) {
+    ref_pool.reserve(n);
     std::vector<int> all(n);
     std::iota(all.begin(), all.end(), 0);
-    RefBuilder rb{P, pool};
-    int root = rb.build(all, 0, n);
+    RefBuilder rb{P, ref_pool};
+    ref_root = rb.build(all, 0, n);
+    int next = 0;
     std::function<void(int)> walk = [&](int bi) {
-      const BNode& b = pool[bi];
-      if (b.leaf) { for (int pi : b.prims) fl.push_slot(pi); return; }
+      const BNode& b = ref_pool[bi];
+      if (b.leaf) { for (int pi : b.prims) rank[pi] = next++; return; }
       walk(b.left);
       walk(b.right);
     };
-    walk(root);
+    walk(ref_root);
+  }
+  Flattener fl{P, kind == BVH_SAH ? pool : ref_pool, S, rank};
+  if (kind == BVH_LIST) {
+    // Slots in the reference's visiting order; only the box tests are dropped, which cannot
+    // change a nearest hit when no box is inverted.
+    std::vector<int> by_rank(n);
+    for (uint32_t i = 0; i < n; ++i) by_rank[rank[i]] = (int)i;
+    for (int pi : by_rank) fl.push_slot(pi);
     S.n_unbounded = (int)n; // every slot is "always tested"
   } else if (kind == BVH_REFERENCE) {
-    pool.reserve(n);
-    std::vector<int> all(n);
-    std::iota(all.begin(), all.end(), 0);
-    RefBuilder rb{P, pool};
-    int root = rb.build(all, 0, n);
     // node 0 = super-root: the reference tests the root's own box first (bvh.ts:130)
     S.nodes.emplace_back();
-    fl.fill_pair(0, root, -1, 0);
+    fl.fill_pair(0, ref_root, -1, 0);
   } else {
     std::vector<int> bounded;
     for (uint32_t i = 0; i < n; ++i) {

@@ -19,7 +19,7 @@ struct HostScene {
   int planar_any = 0;
   int max_depth = 0; // deepest leaf below node 0
   std::vector<Node> nodes;
-  std::vector<F4> p0, p1, p2;
+  std::vector<F4> p0, p1, p2, p3;
   std::vector<I2> slot_info;
   std::vector<ExactPrim> exact;
   std::vector<F4> matA, matE;

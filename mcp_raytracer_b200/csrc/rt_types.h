@@ -7,6 +7,8 @@
 //                                          A = v x w, B = w x u  =>  alpha = p.A - q.A,
 //                                          beta = p.B - q.B  (plane.ts:71-74 rewritten by the
 //                                          scalar-triple-product identity)
+//   p3      [n_slots]  float4              planar only: (|A|_1, |B|_1, 4eps|q.A|, 4eps|q.B|), the
+//                                          per-primitive constants of the FP32 error bound
 //   slot_info [n_slots] int2               (material root, original object index | type<<30)
 //   exact   [n_slots]  ExactPrim 96 B      FP32 vectors + FP64 scalars exactly as the reference
 //                                          holds them; touched only by the guarded FP64 re-test
@@ -46,20 +48,22 @@ struct alignas(16) Node { // 64 B
   float lmin[3], lmax[3];
   float rmin[3], rmax[3];
   int left, right;
-  int pad0, pad1;
+  int flags; // bit0/bit1: left/right subtree holds an inverted box => test it with the reference's per-axis rule
+  int pad1;
 };
 
 struct alignas(16) ExactPrim { // 96 B
   float q[3];  // sphere centre | planar corner
   float u[3], v[3], n[3], w[3];
   int type;
+  int rank;    // position in the reference's visiting order (tie-break on exactly equal t)
   double D;    // plane.ts:39
   double r;    // sphere radius (JS double)
   double area; // quad.ts:37
 };
 
 struct alignas(16) DevLight { // light = object with light:true that is a Sphere or a Quad (scenes.ts:74-79)
-  F4 p0, p1, p2;  // same records as the slot arrays
+  F4 p0, p1, p2, p3;  // same records as the slot arrays
   float q[3], u[3], v[3];
   float area;     // quad
   float radius;   // sphere
@@ -83,6 +87,7 @@ struct DevScene {
   const F4* p0;
   const F4* p1;
   const F4* p2;
+  const F4* p3;
   const I2* slot_info;
   const ExactPrim* exact;
   const F4* matA;

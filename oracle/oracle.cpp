@@ -104,10 +104,12 @@ static inline double illuminance(V3 c) { return 0.299 * c.x + 0.587 * c.y + 0.11
 // Random numbers.  The reference draws from V8's Math.random (unseedable), in a fixed
 // program order per path.  The oracle keeps that draw ORDER and offers two sources:
 //   mode 0  "path-keyed Philox": Philox4x32-10, key=(pixel index, sample index),
-//           counter=(block, stream, seed_lo, seed_hi); stream 0 = camera ray, stream 1+b =
-//           the rayColor call entered with stats.bounces == b; draw i of a stream is word
-//           i&3 of block i>>2, mapped to (w>>8)*2^-24.  The CUDA path uses the same
-//           streams, so a GPU path and an oracle path see the same numbers.
+//           counter=(block, stream, seed_lo, seed_hi); stream b serves the rayColor call
+//           entered with stats.bounces == b, and the camera-ray draws of a path are the first
+//           draws of its stream 0.  A block yields FIVE 24-bit uniforms u*2^-24: the high 24
+//           bits of each of the four words, then one assembled from the low bytes of words
+//           0..2; draw i of a stream is uniform i%5 of block i/5.  The CUDA path uses the
+//           same streams, so a GPU path and an oracle path see the same numbers.
 //   mode 1  sequential xorshift128+ (one stream per render strip, like one Math.random per
 //           worker thread), for independence checks.
 // ----------------------------------------------------------------------------------------
@@ -134,7 +136,7 @@ struct Rng {
   // mode 0
   uint32_t key[2] = {0, 0};
   uint32_t stream = 0, idx = 0;
-  uint32_t buf[4] = {0, 0, 0, 0};
+  uint32_t buf[5] = {0, 0, 0, 0, 0};
   // mode 1
   uint64_t s0 = 1, s1 = 2;
   uint64_t draws = 0;
@@ -164,13 +166,16 @@ struct Rng {
   double next() {
     ++draws;
     if (mode == 0) {
-      if ((idx & 3u) == 0) {
-        uint32_t ctr[4] = {idx >> 2, stream, (uint32_t)seed, (uint32_t)(seed >> 32)};
-        philox4x32_10(ctr, key, buf);
+      if (idx % 5u == 0) {
+        uint32_t ctr[4] = {idx / 5u, stream, (uint32_t)seed, (uint32_t)(seed >> 32)};
+        uint32_t w[4];
+        philox4x32_10(ctr, key, w);
+        for (int k = 0; k < 4; ++k) buf[k] = w[k] >> 8;
+        buf[4] = ((w[0] & 0xffu) << 16) | ((w[1] & 0xffu) << 8) | (w[2] & 0xffu);
       }
-      uint32_t w = buf[idx & 3u];
+      uint32_t v = buf[idx % 5u];
       ++idx;
-      return (double)(w >> 8) * (1.0 / 16777216.0);
+      return (double)v * (1.0 / 16777216.0);
     }
     uint64_t a = s0, b = s1;
     s0 = b;
@@ -806,7 +811,7 @@ struct Camera {
   }
 
   V3 rayColor(const Ray& r, V3 throughput, int& bounces, Rng& g) const { // camera.ts:221-319
-    g.begin_stream(1u + (uint32_t)bounces);
+    if (bounces > 0) g.begin_stream((uint32_t)bounces); // stream 0 continues after the camera-ray draws
     if (bounces >= depth) return mk(0, 0, 0);
     if (roulette && bounces >= rouletteDepth) {
       CNT(rr);

@@ -140,7 +140,7 @@ class OracleCamera:
         rgb = np.zeros((H, W, 3), np.uint8)
         lin = np.zeros((H, W, 3), np.float32)
         mom = np.zeros((H, W, 8), np.float64) if want_moments else None
-        cnt = np.zeros(len(COUNTER_NAMES), np.uint64) if want_counters else None
+        cnt = np.zeros(len(COUNTER_NAMES), np.uint64)  # always on: stats.rays is an event count
         st = rt_stats()
         rc = lib().orc_render_region(self.h, C.byref(reg), rgb.ctypes.data, rgb.nbytes, lin.ctypes.data,
                                      mom.ctypes.data if mom is not None else None, C.byref(st), rng_mode, seed, threads,

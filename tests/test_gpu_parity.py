@@ -1,0 +1,337 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs (north_star bars: primary hits exact on object id and within 1e-4 relative
+on t / normal; converged images within 1% RMSE and 3 sigma per pixel).
+
+Run on the B200 box with `-m gpu`.  Nothing here reads /root/reference.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+from mcp_raytracer_b200 import (
+    Camera, RaytracerError, RenderStats, createCameraFromSceneData, generateCornellSceneData, generateDefaultSceneData,
+    generateLayeredMixedSceneData, generateRainSceneData, generateSpheresSceneData, generateWeekendFinalSceneData,
+    renderScene,
+)
+from mcp_raytracer_b200 import _native
+from mcp_raytracer_b200.scene_data import FlatScene, merge_render_options, render_opts_struct, rt_render_opts, rt_scene_desc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+SCENES = {
+    "C1-spheres": lambda: generateSpheresSceneData({"count": 100, "seed": 12345}),
+    "C2-cornell": generateCornellSceneData,
+    "C3-weekend": generateWeekendFinalSceneData,
+    "C4-rain": lambda: generateRainSceneData({"count": 20000, "seed": 1, "sphereRadius": 0.01}),
+    "C5-layered": generateLayeredMixedSceneData,
+    "default": generateDefaultSceneData,
+}
+
+
+def gpu_render(sd, opts, want_moments=False, region=None):
+    with createCameraFromSceneData(sd, opts) as cam:
+        W, H = cam.imageWidth, cam.imageHeight
+        rgb = np.zeros((H, W, 3), np.uint8)
+        lin = np.zeros((H, W, 3), np.float32)
+        mom = np.zeros((H, W, 8), np.float32) if want_moments else None
+        st = cam.renderRegion(rgb, region, lin, mom)
+    return {"rgb8": rgb, "linear": lin, "moments": mom, "stats": st}
+
+
+# ------------------------------------------------------------------------------------------
+# primary visibility: exact object id, 1e-4 relative on t and normal
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("bvh", ["auto", "reference", "sah"])
+def test_primary_hits_match_oracle(gpu, name, bvh):
+    sd = SCENES[name]()
+    opts = {"width": 384, "samples": 1, "bvh": bvh}
+    with createCameraFromSceneData(sd, opts) as cam:
+        ids, t, nrm, ff = cam.tracePrimary()
+        kind = cam.info.bvh_kind
+    oc = ob.OracleCamera(sd, opts)
+    oids, ot, onrm, off = oc.trace_primary()
+    has_negative = any(o.get("r", 1) < 0 for o in sd["objects"])
+    if kind == 2 and has_negative:
+        # a SAH tree cannot reproduce the inverted-box quirk of negative-radius spheres
+        # (SURVEY.md App. A.4); AUTO never picks SAH for such scenes.
+        pytest.skip("forced SAH on a scene with a negative-radius sphere")
+    assert np.array_equal(ids, oids), f"{int((ids != oids).sum())} primary-hit ids differ ({name}, bvh kind {kind})"
+    hit = oids >= 0
+    assert np.all(np.abs(t[hit] - ot[hit]) <= 1e-4 * np.abs(ot[hit]))
+    assert np.all(np.abs(nrm[hit] - onrm[hit]) <= 1e-4 * 2)  # unit normals: 1e-4 relative
+    assert np.array_equal(ff[hit], off[hit])
+    assert np.all(np.isinf(t[~hit]))
+
+
+def test_primary_hits_full_size_C1(gpu):
+    """BASELINE.json configs[0] at its full size (400x225)."""
+    sd = SCENES["C1-spheres"]()
+    opts = {"width": 400, "samples": 16, "depth": 10}
+    with createCameraFromSceneData(sd, opts) as cam:
+        assert (cam.imageWidth, cam.imageHeight) == (400, 225)
+        ids, t, nrm, _ = cam.tracePrimary()
+    oids, ot, onrm, _ = ob.OracleCamera(sd, opts).trace_primary()
+    assert np.array_equal(ids, oids)
+    hit = oids >= 0
+    assert np.all(np.abs(t[hit] - ot[hit]) <= 1e-4 * np.abs(ot[hit]))
+
+
+def test_primary_hits_match_committed_golden(gpu):
+    """Against the committed fixture (tests/golden/primary_*.npz, made by tests/golden/make_golden.py)."""
+    for name in ("C2-cornell", "default"):
+        f = np.load(os.path.join(GOLDEN, f"primary_{name}.npz"))
+        sd = SCENES[name]()
+        with createCameraFromSceneData(sd, {"width": int(f["width"]), "samples": 1}) as cam:
+            ids, t, nrm, _ = cam.tracePrimary()
+        assert np.array_equal(ids, f["ids"])
+        hit = f["ids"] >= 0
+        assert np.all(np.abs(t[hit] - f["t"][hit]) <= 1e-4 * np.abs(f["t"][hit]))
+        assert np.all(np.abs(nrm[hit] - f["normal"][hit]) <= 2e-4)
+
+
+def test_camera_block_matches_oracle(gpu):
+    for name in ("C2-cornell", "C3-weekend", "default"):
+        sd = SCENES[name]()
+        opts = {"width": 320, "samples": 4}
+        oc = ob.OracleCamera(sd, opts)
+        with createCameraFromSceneData(sd, opts) as cam:
+            assert (cam.imageWidth, cam.imageHeight) == (oc.imageWidth, oc.imageHeight)
+            for a, b in ((cam.center, oc.center), (cam.pixel00Loc, oc.pixel00Loc), (cam.pixelDeltaU, oc.pixelDeltaU),
+                         (cam.pixelDeltaV, oc.pixelDeltaV), (cam.u, oc.u), (cam.v, oc.v), (cam.w, oc.w),
+                         (cam.defocusDiskU, oc.defocusDiskU), (cam.defocusDiskV, oc.defocusDiskV)):
+                assert np.array_equal(a, b)  # bit-exact FP32
+            assert cam.focusDistance == oc.focusDistance
+            assert cam.nLights == oc.n_lights
+
+
+# ------------------------------------------------------------------------------------------
+# same random streams: GPU paths and oracle paths see the same numbers
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,width,spp", [("C2-cornell", 96, 64), ("C1-spheres", 160, 32), ("C5-layered", 96, 64), ("default", 128, 48), ("C3-weekend", 160, 32)])
+def test_same_seed_render_agrees_per_pixel(gpu, name, width, spp):
+    sd = SCENES[name]()
+    opts = {"width": width, "samples": spp, "aTolerance": 0, "seed": 11}
+    g = gpu_render(sd, opts)
+    o = ob.OracleCamera(sd, opts).render(seed=11, threads=8)
+    gs, os_ = g["stats"], o["stats"]
+    assert gs.pixels == os_.pixels and gs.samples["total"] == os_.samples_total
+    assert gs.samples["min"] == os_.samples_min and gs.samples["max"] == os_.samples_max
+    # FP32 vs FP64-scalar arithmetic flips a branch on a tiny fraction of paths; everything
+    # else follows the identical path, so totals agree far inside statistical noise
+    assert abs(gs.bounces["total"] - os_.bounces_total) <= 0.005 * os_.bounces_total + 50
+    assert abs(gs.rays - os_.rays) <= 0.005 * os_.rays + 50
+    d = np.abs(g["linear"].astype(np.float64) - o["linear"].astype(np.float64))
+    scale = np.maximum(o["linear"].astype(np.float64), 0.05)
+    frac_close = float(np.mean((d / scale) < 0.02))
+    assert frac_close > 0.97, f"only {frac_close:.3f} of channels within 2% of the oracle"
+    assert abs(float(g["linear"].mean()) - float(o["linear"].mean())) < 0.01 * float(o["linear"].mean()) + 1e-4
+    # gamma + quantisation of identical colours is identical (camera.ts:455-472)
+    same = d.max(axis=2) == 0
+    assert np.array_equal(g["rgb8"][same], o["rgb8"][same])
+    assert float(np.mean(np.abs(g["rgb8"].astype(int) - o["rgb8"].astype(int)) <= 2)) > 0.97
+
+
+# ------------------------------------------------------------------------------------------
+# independent random streams: the statistical bar of the north star
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,width,spp", [("C2-cornell", 64, 1024), ("C1-spheres", 96, 1024), ("C5-layered", 48, 1024)])
+def test_converged_image_rmse_and_3sigma(gpu, name, width, spp):
+    sd = SCENES[name]()
+    opts = {"width": width, "samples": spp, "aTolerance": 0}
+    g = gpu_render(sd, {**opts, "seed": 1}, want_moments=True)
+    o = ob.OracleCamera(sd, opts).render(seed=2, threads=8, want_moments=True)
+    gm, om = g["moments"].astype(np.float64), o["moments"]
+    n = float(spp)
+    g_mean, o_mean = gm[..., 0:3] / n, om[..., 0:3] / n
+    g_var = np.maximum(gm[..., 3:6] / n - g_mean**2, 0) * n / (n - 1)
+    o_var = np.maximum(om[..., 3:6] / n - o_mean**2, 0) * n / (n - 1)
+    # 1% relative RMSE of the image, after removing the Monte-Carlo noise both estimates carry
+    mse = float(np.mean((g_mean - o_mean) ** 2))
+    noise = float(np.mean(g_var / n + o_var / n))
+    excess = max(mse - noise, 0.0)
+    ref_rms = float(np.sqrt(np.mean(o_mean**2)))
+    assert np.sqrt(excess) <= 0.01 * ref_rms, f"bias RMSE {np.sqrt(excess):.5f} vs 1% of {ref_rms:.4f}"
+    # per pixel: |difference| <= 3 sigma of the difference of two independent estimates
+    sigma = np.sqrt(g_var / n + o_var / n)
+    ok = np.abs(g_mean - o_mean) <= 3 * sigma + 1e-6
+    # heavy-tailed per-sample radiance (fireflies) makes the sample variance an underestimate on a
+    # few pixels; a Gaussian would leave 0.27% outside
+    assert float(np.mean(ok)) >= 0.985, f"{float(np.mean(ok)):.4f} of channels within 3 sigma"
+    # RGB8 after gamma: the two images differ by Monte-Carlo noise only.  d(255.999*sqrt(c)) =
+    # 128*dc/sqrt(c), so compare the mean level difference with what the measured sigma predicts.
+    expected = 128.0 * np.sqrt(2 / np.pi) * sigma / np.sqrt(np.maximum(o_mean, 1e-3))
+    got = np.abs(g["rgb8"].astype(int) - o["rgb8"].astype(int))
+    assert float(np.mean(got)) <= 1.5 * float(np.mean(expected)) + 0.5
+
+
+def test_white_furnace_energy(gpu):
+    """Analytic check that pins BOTH sides: inside a closed emissive-free sphere of
+    albedo a lit by a uniform background seen through nothing — here: an open scene with a
+    constant background L and one Lambertian sphere of albedo a: every path that escapes carries
+    a^k L, so the radiance of a camera ray that hits the sphere lies in (0, L] and a miss is L."""
+    sd = {
+        "camera": {"vfov": 40, "from": [0, 0, 3], "at": [0, 0, 0], "up": [0, 1, 0], "aperture": 0, "focus": 1,
+                   "background": {"type": "gradient", "top": [0.5, 0.5, 0.5], "bottom": [0.5, 0.5, 0.5]}},
+        "materials": [{"id": "m", "material": {"type": "lambert", "color": [1.0, 1.0, 1.0]}}],
+        "objects": [{"type": "sphere", "pos": [0, 0, 0], "r": 1.0, "material": "m"}],
+    }
+    opts = {"width": 48, "aspect": 1.0, "samples": 256, "aTolerance": 0, "roulette": False, "depth": 64}
+    g = gpu_render(sd, opts)
+    # albedo 1, convex object, constant environment: every pixel converges to exactly L
+    assert np.allclose(g["linear"], 0.5, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# regions, partitions, determinism
+# ------------------------------------------------------------------------------------------
+def test_render_is_deterministic_and_seeded(gpu):
+    sd = SCENES["C2-cornell"]()
+    a = gpu_render(sd, {"width": 64, "samples": 8, "aTolerance": 0, "seed": 5})
+    b = gpu_render(sd, {"width": 64, "samples": 8, "aTolerance": 0, "seed": 5})
+    c = gpu_render(sd, {"width": 64, "samples": 8, "aTolerance": 0, "seed": 6})
+    assert np.array_equal(a["linear"], b["linear"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    assert not np.array_equal(a["linear"], c["linear"])
+
+
+def test_region_writes_only_region_pixels(gpu):  # camera.ts:388-431, camera.test.ts:381-396
+    sd = SCENES["C2-cornell"]()
+    opts = {"width": 80, "samples": 4, "aTolerance": 0, "seed": 3}
+    full = gpu_render(sd, opts)
+    with createCameraFromSceneData(sd, opts) as cam:
+        buf = np.full((cam.imageHeight, cam.imageWidth, 3), 77, np.uint8)
+        st = cam.renderRegion(buf, {"x": 10, "y": 20, "width": 30, "height": 25})
+        assert st.pixels == 30 * 25 and st.samples["total"] == 30 * 25 * 4
+        inside = np.zeros(buf.shape[:2], bool)
+        inside[20:45, 10:40] = True
+        assert np.all(buf[~inside] == 77)
+        assert np.array_equal(buf[inside], full["rgb8"][inside])  # RNG keyed by global pixel index
+        st = cam.renderRegion(buf, {"x": 70, "y": 70, "width": 30, "height": 30})  # clipped (camera.ts:390-391)
+        assert st.pixels == 100
+        st = cam.renderRegion(buf, {"x": 200, "y": 0, "width": 10, "height": 10})
+        assert st.pixels == 0 and st.samples["min"] == float("inf")
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_tile_partition_union_equals_whole_image(gpu, parts):
+    """The multi-GPU partition (interleaved 16x16 tiles) rendered part by part on one GPU."""
+    sd = SCENES["C2-cornell"]()
+    opts = {"width": 100, "samples": 4, "aTolerance": 0, "seed": 9}
+    whole = gpu_render(sd, opts)
+    H, W = whole["rgb8"].shape[:2]
+    buf = np.zeros((H, W, 3), np.uint8)
+    stats = []
+    for k in range(parts):
+        with createCameraFromSceneData(sd, {**opts, "partIndex": k, "partCount": parts}) as cam:
+            stats.append(cam.render(buf))
+    assert np.array_equal(buf, whole["rgb8"])
+    m = RenderStats.merge(stats)
+    ws = whole["stats"]
+    assert (m.pixels, m.samples["total"], m.bounces["total"], m.rays) == (ws.pixels, ws.samples["total"], ws.bounces["total"], ws.rays)
+    assert (m.bounces["min"], m.bounces["max"]) == (ws.bounces["min"], ws.bounces["max"])
+
+
+def test_row_strip_regions_like_the_reference_workers(gpu):  # raytracer.ts:185-205
+    from mcp_raytracer_b200 import divideIntoRegions
+
+    sd = SCENES["C1-spheres"]()
+    opts = {"width": 120, "samples": 2, "aTolerance": 0}
+    whole = gpu_render(sd, opts)
+    with createCameraFromSceneData(sd, opts) as cam:
+        buf = np.zeros((cam.imageHeight, cam.imageWidth, 3), np.uint8)
+        stats = [cam.renderRegion(buf, r) for r in divideIntoRegions(cam.imageWidth, cam.imageHeight, 7)]
+    assert np.array_equal(buf, whole["rgb8"])
+    assert RenderStats.merge(stats).pixels == whole["stats"].pixels
+
+
+# ------------------------------------------------------------------------------------------
+# adaptive sampling, render modes, depth / roulette options
+# ------------------------------------------------------------------------------------------
+def test_adaptive_sampling_matches_oracle(gpu):  # camera.ts:348-368, :406
+    sd = SCENES["C1-spheres"]()
+    opts = {"width": 160, "samples": 100, "aTolerance": 0.05, "aBatch": 10, "seed": 4}
+    g = gpu_render(sd, opts)
+    o = ob.OracleCamera(sd, opts).render(seed=4, threads=8)
+    gs, os_ = g["stats"], o["stats"]
+    assert gs.samples["min"] == os_.samples_min == 10       # flat background pixels stop at aBatch
+    assert gs.samples["max"] == os_.samples_max
+    assert abs(gs.samples["total"] - os_.samples_total) <= 0.01 * os_.samples_total
+    assert gs.samples["total"] < 0.8 * gs.pixels * 100      # adaptive exit really saves samples
+
+
+def test_render_modes(gpu):  # camera.ts:326-340
+    sd = SCENES["C1-spheres"]()
+    base = {"width": 96, "samples": 40, "aTolerance": 0.05, "seed": 2}
+    for mode in ("bounces", "samples"):
+        g = gpu_render(sd, {**base, "mode": mode})
+        o = ob.OracleCamera(sd, {**base, "mode": mode}).render(seed=2, threads=8)
+        lin, olin = g["linear"], o["linear"]
+        if mode == "bounces":
+            assert np.all(lin[..., 0] == 0) and np.all(lin[..., 1] == 0)
+            assert abs(float(lin[..., 2].mean()) - float(olin[..., 2].mean())) < 0.02 * float(olin[..., 2].mean()) + 1e-4
+        else:
+            assert np.all(lin[..., 1] == 0) and np.all(lin[..., 2] == 0)
+            assert float(np.mean(lin[..., 0] == olin[..., 0])) > 0.97
+        assert float(np.mean(np.abs(g["rgb8"].astype(int) - o["rgb8"].astype(int)) <= 1)) > 0.97
+
+
+def test_depth_limit_and_roulette_options(gpu):  # camera.ts:228-245, camera.test.ts:591-655
+    sd = SCENES["C2-cornell"]()
+    a = gpu_render(sd, {"width": 48, "samples": 16, "aTolerance": 0, "depth": 3, "roulette": False})["stats"]
+    assert a.bounces["max"] <= 3
+    b = gpu_render(sd, {"width": 48, "samples": 16, "aTolerance": 0, "depth": 30, "roulette": False})["stats"]
+    c = gpu_render(sd, {"width": 48, "samples": 16, "aTolerance": 0, "depth": 30, "roulette": True, "rouletteDepth": 3})["stats"]
+    assert c.bounces["total"] < b.bounces["total"] and b.bounces["max"] <= 30
+    d = gpu_render(sd, {"width": 48, "samples": 1, "aTolerance": 0})["stats"]  # samples == 1: no jitter (camera.ts:184)
+    assert d.samples["total"] == d.pixels
+
+
+def test_stats_10x10_one_sample(gpu):  # camera.test.ts:332-357
+    sd = SCENES["C1-spheres"]()
+    st = gpu_render(sd, {"width": 10, "aspect": 1.0, "samples": 1})["stats"]
+    assert (st.pixels, st.samples["total"], st.samples["min"], st.samples["max"], st.samples["avg"]) == (100, 100, 1, 1, 1)
+
+
+def test_output_dimensions_like_raytracer_tests(gpu):  # raytracer.test.ts:38-173
+    for width, aspect, (W, H) in ((10, 1.0, (10, 10)), (8, 2.0, (8, 4)), (16, 1.0, (16, 16)), (20, 2.0, (20, 10)), (30, 1.5, (30, 20))):
+        rgb, st = renderScene({"type": "default", "render": {"width": width, "aspect": aspect, "samples": 2}})
+        assert rgb.shape == (H, W, 3) and st.pixels == W * H
+    rgb, st = renderScene({"type": "spheres", "options": {"count": 5, "seed": 3}, "render": {"width": 12, "aspect": 1.0, "samples": 2}},
+                          {"parallel": True, "threads": 2})
+    assert rgb.shape == (12, 12, 3) and st.pixels == 144
+
+
+# ------------------------------------------------------------------------------------------
+# error behaviour through the C ABI (scenes.ts:137,154,178,191,195; raytracer.ts:97-99)
+# ------------------------------------------------------------------------------------------
+def test_c_abi_error_codes(gpu):
+    L = _native.lib()
+    sd = SCENES["C2-cornell"]()
+    fs = FlatScene(sd)
+    opts = render_opts_struct(merge_render_options(sd.get("render"), {"width": 32, "samples": 1}))
+    h = C.c_void_p()
+    assert L.rt_camera_create(None, C.byref(opts), C.byref(h)) == 1
+    fs.obj_type[0] = 9
+    assert L.rt_camera_create(C.byref(fs.desc), C.byref(opts), C.byref(h)) == 2 and b"Unknown object type" in L.rt_last_error()
+    fs.obj_type[0] = 2
+    fs.mat_type_a[0] = 17
+    assert L.rt_camera_create(C.byref(fs.desc), C.byref(opts), C.byref(h)) == 3 and b"Unknown material type" in L.rt_last_error()
+    fs.mat_type_a[0] = 0
+    fs.obj_material[0] = 99
+    assert L.rt_camera_create(C.byref(fs.desc), C.byref(opts), C.byref(h)) == 4 and b"Material not found" in L.rt_last_error()
+    fs.obj_material[0] = 0
+    assert L.rt_camera_create(C.byref(fs.desc), C.byref(opts), C.byref(h)) == 0
+    small = np.zeros(10, np.uint8)
+    from mcp_raytracer_b200.scene_data import rt_stats
+    st = rt_stats()
+    assert L.rt_camera_render(h, small.ctypes.data, small.nbytes, None, C.byref(st)) == 6  # buffer too small
+    assert L.rt_camera_destroy(h) == 0
+    with pytest.raises(RaytracerError, match="Material is not a dielectric"):
+        bad = generateDefaultSceneData()
+        bad["materials"][5]["material"]["outer"] = {"type": "lambert", "color": [1, 1, 1]}
+        createCameraFromSceneData(bad, {"width": 16})

@@ -1,0 +1,134 @@
+"""CPU-side checks of the boundary: the C-ABI library loads and exports every symbol
+include/rt_b200.h declares (no compute without a GPU), fails loudly without a device, and the
+multi-rank plumbing works over gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mcp_raytracer_b200 import _native
+
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_native.EXPORTS), declared ^ set(_native.EXPORTS)
+    lib = _native.lib()
+    for s in declared:
+        assert hasattr(lib, s), f"{s} not exported by {_native.LIB_PATH}"
+    assert lib.rt_abi_version() == 1
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _native.LIB_PATH]).decode()
+    exported_rt = {l.split()[-1] for l in out.splitlines() if " T rt_" in l}
+    assert declared <= exported_rt
+
+
+def test_library_is_built_for_sm_100a():
+    from mcp_raytracer_b200 import _native
+
+    out = subprocess.check_output(["cuobjdump", "--list-elf", _native.LIB_PATH]).decode()
+    assert "sm_100a" in out
+
+
+def test_struct_layouts_match_the_header():
+    """sizeof of every ctypes mirror equals the C compiler's (guards the ABI)."""
+    from mcp_raytracer_b200 import scene_data as sd
+
+    src = r'''
+    #include <stdio.h>
+    #include "rt_b200.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(rt_camera_desc), sizeof(rt_scene_desc), sizeof(rt_render_opts),
+                           sizeof(rt_region), sizeof(rt_stats), sizeof(rt_camera_info)); return 0; }'''
+    exe = os.path.join("/tmp", f"rt_sizes_{os.getpid()}")
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    os.remove(exe)
+    mine = [C.sizeof(t) for t in (sd.rt_camera_desc, sd.rt_scene_desc, sd.rt_render_opts, sd.rt_region, sd.rt_stats, sd.rt_camera_info)]
+    assert sizes == mine
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must fail loudly, never fall back."""
+    from mcp_raytracer_b200 import RaytracerError, createCameraFromSceneData, generateCornellSceneData, _native
+
+    if _native.lib().rt_device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    with pytest.raises(RaytracerError, match="no CPU fallback"):
+        createCameraFromSceneData(generateCornellSceneData(), {"width": 16})
+
+
+def test_scene_errors_are_reported_before_device_checks():
+    from mcp_raytracer_b200 import _native
+    from mcp_raytracer_b200.scene_data import FlatScene, merge_render_options, render_opts_struct
+    from mcp_raytracer_b200.scenes import generateCornellSceneData
+
+    L = _native.lib()
+    sd = generateCornellSceneData()
+    fs = FlatScene(sd)
+    opts = render_opts_struct(merge_render_options(sd.get("render"), {"width": 32}))
+    h = C.c_void_p()
+    fs.mat_child_a  # noqa: B018
+    fs.obj_type[3] = 7
+    assert L.rt_camera_create(C.byref(fs.desc), C.byref(opts), C.byref(h)) == 2
+    assert b"Unknown object type" in L.rt_last_error()
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is the checker: nothing under the product package may import, link or open it."""
+    pkg = os.path.join(ROOT, "mcp_raytracer_b200")
+    for dp, _dn, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dp, fn), errors="replace").read()
+                assert "oracle_binding" not in txt and "liboracle" not in txt and "oracle/" not in txt, os.path.join(dp, fn)
+
+
+def test_tile_owner_mask_partitions_the_image():
+    from mcp_raytracer_b200.distributed import tile_owner_mask
+
+    for W, H, n in ((100, 70, 2), (1024, 1024, 8), (33, 17, 3)):
+        total = np.zeros((H, W), int)
+        for k in range(n):
+            total += tile_owner_mask(W, H, k, n)
+        assert np.all(total == 1)
+    counts = [tile_owner_mask(1024, 1024, k, 8).sum() for k in range(8)]
+    assert max(counts) - min(counts) <= 0.01 * 1024 * 1024  # balanced
+
+
+_WORKER = r'''
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from mcp_raytracer_b200.distributed import tile_owner_mask, gather_framebuffer, merge_stats
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+W, H = 100, 52
+rng = np.random.default_rng(0)
+whole = rng.integers(1, 255, (H, W, 3), dtype=np.uint8)          # what a 1-rank render would produce
+mine = np.where(tile_owner_mask(W, H, rank, world)[..., None], whole, 0).astype(np.uint8)
+t = gather_framebuffer(torch.from_numpy(mine.copy()))
+sums = torch.tensor([int(tile_owner_mask(W, H, rank, world).sum()), 10 * (rank + 1)], dtype=torch.int64)
+mins = torch.tensor([rank + 3], dtype=torch.int64); maxs = torch.tensor([rank + 7], dtype=torch.int64)
+merge_stats(sums, mins, maxs)
+if rank == 0:
+    assert np.array_equal(t.numpy(), whole), "gathered framebuffer differs"
+    assert sums.tolist() == [W * H, 10 * sum(range(1, world + 1))] and mins.item() == 3 and maxs.item() == world + 6
+    print("GATHER_OK")
+dist.destroy_process_group()
+'''
+
+
+def test_gloo_world_size_2_gather_and_stats(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29613", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert "GATHER_OK" in outs[0]
