@@ -16,6 +16,9 @@ namespace rt {
 
 static constexpr int kTile = 16;
 static constexpr int kListMax = 64;
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 2
+#endif
 
 RT_DEV unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
@@ -81,7 +84,7 @@ RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
 // the lean variant is the fixed-spp default-mode path the benchmark configs run.
 // =========================================================================================
 template <int KIND, bool FULL>
-__global__ void __launch_bounds__(256, 2) k_render_mega(const DevScene S, const RenderParams R) {
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_mega(const DevScene S, const RenderParams R) {
   __shared__ ListSmem sm;
   const SmemList L = stage_list<KIND>(S, sm);
   const DevCamera& cam = S.cam;
