@@ -14,7 +14,7 @@ from .scene_data import rt_camera_info, rt_region, rt_render_opts, rt_scene_desc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libmcprt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(CSRC, "libmcprt_b200.so")  # env: A/B-test another build
 
 # every symbol include/rt_b200.h declares
 EXPORTS = [

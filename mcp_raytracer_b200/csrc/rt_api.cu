@@ -15,7 +15,9 @@
 #include "rt_types.h"
 
 namespace rt {
-cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, cudaStream_t st);
+cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st);
+void render_tile_grid(const RenderParams& R, int* tiles_x, int* tiles_y);
+bool render_needs_full(const DevScene& S, const RenderParams& R);
 cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* obj_id, float* t, float* normal,
                                  uint8_t* front, cudaStream_t st);
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
@@ -67,6 +69,13 @@ struct rt_camera {
   float* d_normal = nullptr;
   uint8_t* d_front = nullptr;
   unsigned long long* d_stats = nullptr;
+  // work queue of the render kernel: [0] = next item, [1..] = finished chunks per tile
+  int* d_queue = nullptr;
+  size_t queue_ints = 0;
+  unsigned long long* d_scratch = nullptr; // fixed-point radiance sums [H][W][4]
+  size_t scratch_elems = 0;
+  int sms = 0;
+  int chunks = 1;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -87,7 +96,7 @@ static void free_camera(rt_camera* c) {
   DeviceGuard g(c->device);
   for (void* p : c->allocs) cudaFree(p);
   cudaFree(c->d_rgb8); cudaFree(c->d_linear); cudaFree(c->d_moments); cudaFree(c->d_ids);
-  cudaFree(c->d_t); cudaFree(c->d_normal); cudaFree(c->d_front); cudaFree(c->d_stats);
+  cudaFree(c->d_t); cudaFree(c->d_normal); cudaFree(c->d_front); cudaFree(c->d_stats); cudaFree(c->d_queue); cudaFree(c->d_scratch);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -186,6 +195,14 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
     free_camera(c);
     return fail(RT_ERR_CUDA, "allocating stats/events: " + m);
   }
+  cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, dev);
+  {
+    c->chunks = 0; // 0 = chosen per launch (enqueue_render)
+    if (const char* e = getenv("RT_B200_CHUNKS")) { // development override
+      int v = atoi(e);
+      if (v >= 1 && v <= 64) c->chunks = v;
+    }
+  }
   c->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   *out = c;
   return RT_OK;
@@ -224,8 +241,52 @@ rt_status rt_camera_set_stream(rt_camera* c, void* s) {
 static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_dev, int* launches) {
   CU(cudaMemcpyAsync(c->d_stats, kStatsInit, sizeof(kStatsInit), cudaMemcpyHostToDevice, c->stream));
   P.stats = c->d_stats;
-  CU(launch_render_mega(c->ds, P, c->stream));
-  *launches = (P.x1 > P.x0 && P.y1 > P.y0) ? 1 : 0;
+  *launches = 0;
+  if (P.x1 > P.x0 && P.y1 > P.y0) {
+    render_tile_grid(P, &P.tiles_x, &P.tiles_y);
+    if (render_needs_full(c->ds, P)) P.chunks = 1;
+    else if (c->chunks > 0) P.chunks = c->chunks;
+    else {
+      // Sample chunks per pixel: enough (8x4 block, chunk) warp items that the blocks this GPU owns
+      // keep it busy for >= 16 rounds of resident warps, so the tail of the render stays ~1/32 of it
+      // whether the GPU renders the whole image or 1/8 of it.  Sums are exact fixed point, so the
+      // image does not depend on this choice.  A chunk stays <= 2048 samples (limb accumulators).
+      const long long owned = std::max(1LL, (long long)P.tiles_x * P.tiles_y * 8 / std::max(1, P.part_count));
+      const long long target = 16LL * c->sms * 2 * 8;
+      long long k = (target + owned - 1) / owned;
+      k = std::min<long long>(k, std::max(1, c->hs.cam.samples / 16));
+      P.chunks = (int)std::min<long long>(std::max<long long>(k, 1), 64);
+    }
+    if (P.chunks > 1 || !render_needs_full(c->ds, P)) P.chunks = std::max(P.chunks, (c->hs.cam.samples + 2047) / 2048);
+    const size_t need_q = 1 + (size_t)P.tiles_x * P.tiles_y * 8; // queue head + one completion counter per 8x4 block
+    if (need_q > c->queue_ints) {
+      CU(cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_queue);
+      c->d_queue = nullptr;
+      CU(cudaMalloc(&c->d_queue, need_q * sizeof(int)));
+      c->queue_ints = need_q;
+    }
+    // fixed-point radiance sums [H][W][4] u64, only when a pixel's samples are split over CTAs
+    const size_t need_s = P.chunks > 1 ? (size_t)4 * c->hs.image_width * c->hs.image_height : 0;
+    if (need_s > c->scratch_elems) {
+      CU(cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_scratch);
+      c->d_scratch = nullptr;
+      CU(cudaMalloc(&c->d_scratch, need_s * sizeof(unsigned long long)));
+      c->scratch_elems = need_s;
+    }
+    CU(cudaMemsetAsync(c->d_queue, 0, need_q * sizeof(int), c->stream));
+    if (need_s) {
+      // only the rows of the region are touched
+      const size_t row = (size_t)4 * c->hs.image_width;
+      CU(cudaMemsetAsync(c->d_scratch + row * P.y0, 0, row * (size_t)(P.y1 - P.y0) * sizeof(unsigned long long), c->stream));
+    }
+    P.queue = c->d_queue;
+    P.tile_done = c->d_queue + 1;
+    P.accum = c->d_scratch;
+    CU(launch_render_mega(c->ds, P, c->sms, c->stream));
+    *launches = 1;
+  }
   if (stats_dev) {
     CU(launch_finalize_stats(c->d_stats, stats_dev, *launches + 1, c->stream));
     *launches += 1;

@@ -1,15 +1,26 @@
 // rt_megakernel.cu — register-resident path tracer ("megakernel" integrator) and the
 // primary-visibility parity kernel, for sm_100a.
 //
-// Mapping: one CTA = one 16x16 image tile, one thread = one pixel, a warp = an 8x4 pixel
-// block (coherent primary rays).  Each thread runs the reference's per-pixel loop
-// (src/camera.ts:400-423): sample until `samples` or adaptive convergence, accumulate, write.
-// The sample loop and the bounce recursion (src/camera.ts:221-319) are flattened into ONE
-// loop with per-lane path regeneration: a lane whose path ended starts its next sample in
-// the same iteration in which its neighbours trace their next bounce, so every iteration
-// every live lane generates one Philox block, traces exactly one ray and shades one hit, and
-// no lane idles waiting for the longest path of a sample.  All path state lives in registers;
-// HBM sees the scene reads (L1/L2 resident) and 3 bytes per pixel of output.
+// Work decomposition (both render kernels): the image region is cut into 16x16 tiles and every
+// pixel's samples into `chunks` contiguous ranges; a work item is (tile, chunk).  The grid is
+// persistent (resident CTAs only); each CTA pulls items from an atomic queue, so the tail of a render
+// is one item long instead of one wave long, and a GPU that owns only 1/8 of the tiles still fills its
+// SMs evenly.
+//
+// k_render_pool (fixed spp, default mode — the benchmark path): inside an item the 256 x chunk
+// (pixel, sample) pairs form a pool; lanes fetch the next pair with a warp-aggregated atomic (ballot +
+// popc prefix, one shared-memory atomic per warp per fetch) whenever their path ends, so every
+// iteration every lane generates one Philox block, traces exactly one ray and shades one hit — no lane
+// waits for a neighbour's longer path or cheaper pixel.  Radiance is accumulated per pixel in 64-bit
+// fixed point (shared-memory atomics), which is exact and order-independent: the image does not depend
+// on which lane took which sample, on the chunking or on the number of GPUs.
+//
+// k_render_pixels (adaptive sampling / render modes / moments): one thread owns one pixel and runs the
+// reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule requires, with
+// the same per-lane path regeneration.
+//
+// All path state lives in registers; HBM sees the scene reads (L1/L2 resident), 24 B of atomics per
+// (pixel, chunk) when chunks > 1, and 3 bytes per pixel of output.
 #include "rt_device.cuh"
 
 namespace rt {
@@ -36,22 +47,11 @@ RT_DEV int warp_max(int v) {
   return v;
 }
 
-// thread -> pixel inside the tile: warp w covers an 8x4 block
-RT_DEV void tile_pixel(int& px, int& py) {
-  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+// index 0..255 -> pixel inside the tile: each group of 32 covers an 8x4 block
+RT_DEV void tile_pixel(int idx, int& px, int& py) {
+  int lane = idx & 31, w = idx >> 5;
   px = (w & 1) * 8 + (lane & 7);
   py = (w >> 1) * 4 + (lane >> 3);
-}
-
-template <int KIND>
-RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
-  RayPre pre = precompute(r, KIND != BVH_LIST);
-  t = CUDART_INF_F;
-  slot = -1;
-  if (KIND == BVH_LIST) trace_list(S, L, r, pre, t, slot);
-  else if (KIND == BVH_SAH) trace_sah(S, r, pre, t, slot);
-  else trace_ref(S, r, pre, t, slot);
-  return slot >= 0;
 }
 
 struct ListSmem {
@@ -79,204 +79,405 @@ RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
   return L;
 }
 
+template <int KIND>
+RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
+  RayPre pre = precompute(r, KIND != BVH_LIST);
+  t = CUDART_INF_F;
+  slot = -1;
+  if (KIND == BVH_LIST) trace_list(S, L, r, pre, t, slot);
+  else if (KIND == BVH_SAH) trace_sah(S, r, pre, t, slot);
+  else trace_ref(S, r, pre, t, slot);
+  return slot >= 0;
+}
+
+// MixturePDF([cosine, lights...], [0.5, 0.5/n ...]) constants — camera.ts:287-288, pdf.ts:66-72
+struct MixW {
+  int nl;
+  float wl, total_w, inv_total_w;
+};
+RT_DEV MixW make_mixw(const DevScene& S) {
+  MixW m;
+  m.nl = S.n_lights;
+  m.wl = m.nl > 0 ? 0.5f / (float)m.nl : 0.f;
+  m.total_w = 0.5f;
+  for (int k = 0; k < m.nl; ++k) m.total_w += m.wl; // summed like weights.reduce (pdf.ts:71)
+  m.inv_total_w = 1.0f / m.total_w;
+  return m;
+}
+
+struct PathState {
+  Ray ray;
+  V3 tp, radiance;
+  int bounces;
+};
+
+// One rayColor call (camera.ts:221-319) on the path's current ray.  Returns true when the path ended
+// (its radiance is complete); otherwise ps.ray / ps.tp / ps.bounces describe the next call.
+template <int KIND>
+RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
+                      unsigned& rays) {
+  const DevCamera& cam = S.cam;
+  bool done = ps.bounces >= cam.depth;
+  if (!done && cam.roulette && ps.bounces >= cam.rr_depth) { // camera.ts:233-245
+    float p = fminf(maxc(ps.tp), 0.95f);
+    done = g.next() > p;
+    ps.tp = ps.tp * rcp_approx(p);
+  }
+  if (done) return true;
+  float t;
+  int slot;
+  ++rays;
+  if (!closest_hit<KIND>(S, L, ps.ray, t, slot)) { // camera.ts:252-258
+    V3 ud = normalize3(ps.ray.d);
+    float a = 0.5f * (ud.y + 1.0f);
+    V3 bg = ld3(cam.bg_top) * (1.0f - a) + ld3(cam.bg_bottom) * a;
+    ps.radiance = ps.radiance + bg * ps.tp;
+    return true;
+  }
+  int type, root;
+  F4 p0;
+  if (KIND == BVH_LIST) { type = sm.type[slot]; root = sm.mat[slot]; p0 = sm.p0[slot]; }
+  else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
+  const Surf sf = surface_at(type, p0, ps.ray, t);
+  const I4 mb = ldgi4(S.matB + root);
+  const F4 ma = ldg4(S.matA + root);
+  if (mb.w) { // emitted * throughput (camera.ts:261)
+    F4 e = ldg4(S.matE + root);
+    ps.radiance = ps.radiance + xyz(e) * ps.tp;
+  }
+  Scatter sc;
+  if (mb.x == MAT_LAMBERT) { sc.kind = SCATTER_DIFFUSE; sc.attenuation = xyz(ma); sc.dir = mk3(0, 0, 0); }
+  else if (mb.x == MAT_LIGHT) return true; // scatter == null: emitted only, bounce not counted (camera.ts:267-269)
+  else sc = scatter_material(S, root, mb, ma, ps.ray.d, sf, g);
+  if (sc.kind == SCATTER_NONE) return true;
+  ++ps.bounces;
+  if (sc.kind == SCATTER_SPECULAR) { // camera.ts:275-282
+    ps.tp = ps.tp * sc.attenuation;
+    ps.ray = Ray{sf.p, sc.dir};
+    return false;
+  }
+  // camera.ts:285-315 with the mixture pdf of pdf.ts:57-99
+  const Onb onb = make_onb(sf.n);
+  const float rnd = g.next() * mw.total_w;
+  const float r1 = g.next(), r2 = g.next();
+  V3 dir = onb_local(onb, cosine_direction(r1, r2));
+  if (mw.nl > 0) {
+    float partial = 0.5f;
+    int chosen = mw.nl - 1;
+    for (int k = 0; k < mw.nl; ++k) {
+      partial += mw.wl;
+      if (rnd < partial) { chosen = k; break; }
+    }
+    V3 ldir = light_random_vec(S.lights[chosen], sf.p, r1, r2);
+    dir = sel3(rnd < 0.5f, dir, ldir);
+  }
+  const float cz = dot3(dir, onb.w); // all three generators return unit vectors
+  const float cosv = cz <= 0.f ? 0.f : cz * 0.31830988618f;
+  float sum = 0.5f * cosv;
+  for (int k = 0; k < mw.nl; ++k) sum = fmaf(mw.wl, light_pdf_value(S, S.lights[k], sf.p, dir), sum);
+  const float pdf_value = sum * mw.inv_total_w;
+  if (!(pdf_value > 0.0001f)) return true; // camera.ts:298-301 (NaN also ends the path)
+  ps.tp = ps.tp * (sc.attenuation * (cosv * rcp_approx(pdf_value)));
+  ps.ray = Ray{sf.p, dir};
+  return false;
+}
+
+// finalColor (camera.ts:326-340, default mode) + writeColorToBuffer (camera.ts:455-472)
+RT_DEV void write_pixel(const RenderParams& R, size_t pi, V3 fc) {
+  if (R.rgb8) {
+    const float c[3] = {fc.x, fc.y, fc.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double v = floor(255.999 * sqrt((double)c[k]));
+      // Uint8ClampedArray store: NaN/negative -> 0, >255 -> 255
+      R.rgb8[pi * 3 + k] = !(v > 0.0) ? 0 : (v >= 255.0 ? 255 : (uint8_t)v);
+    }
+  }
+  if (R.linear) { R.linear[pi * 3] = fc.x; R.linear[pi * 3 + 1] = fc.y; R.linear[pi * 3 + 2] = fc.z; }
+}
+
+// RenderStats contribution of a lane (renderStats.ts:21-35): warp-reduce, one atomic each.
+// n_pixels pixels were completed, each with pixel_samples samples; n_samples paths were traced.
+RT_DEV void flush_stats(const RenderParams& R, unsigned n_pixels, int pixel_samples, unsigned n_samples, unsigned bounces_sum,
+                        unsigned rays, int min_b, int max_b) {
+  if (!R.stats) return;
+  unsigned long long px = warp_sum((unsigned long long)n_pixels);
+  unsigned long long ss = warp_sum((unsigned long long)n_samples);
+  unsigned long long bs = warp_sum((unsigned long long)bounces_sum);
+  unsigned long long rs = warp_sum((unsigned long long)rays);
+  int smin = warp_min(n_pixels ? pixel_samples : 0x7fffffff), smax = warp_max(n_pixels ? pixel_samples : 0);
+  int bmin = warp_min(n_samples ? min_b : 0x7fffffff), bmax = warp_max(n_samples ? max_b : 0);
+  if ((threadIdx.x & 31) == 0 && (ss || px)) {
+    atomicAdd(R.stats + kStatPixels, px);
+    atomicAdd(R.stats + kStatSamples, ss);
+    atomicAdd(R.stats + kStatBounces, bs);
+    atomicAdd(R.stats + kStatRays, rs);
+    atomicMin(R.stats + kStatSamplesMin, (unsigned long long)smin);
+    atomicMax(R.stats + kStatSamplesMax, (unsigned long long)smax);
+    atomicMin(R.stats + kStatBouncesMin, (unsigned long long)bmin);
+    atomicMax(R.stats + kStatBouncesMax, (unsigned long long)bmax);
+  }
+}
+
+// radiance -> 2^-32 fixed point.  NaN and negatives count as 0, a single sample saturates at 65536
+// (the reference has no clamp; a 15-unit light needs a 4000x throughput spike to get there).
+RT_DEV unsigned long long to_fixed(float x) {
+  x = fminf(fmaxf(x, 0.f), 65536.f); // fmaxf(NaN, 0) = 0
+  return __float2ull_rz(x * 4294967296.f);
+}
+RT_DEV float from_fixed(unsigned long long s, int samples) { return (float)(((double)s * (1.0 / 4294967296.0)) / (double)samples); }
+
 // =========================================================================================
-// render kernel.  FULL = adaptive sampling / render modes / moments output compiled in;
-// the lean variant is the fixed-spp default-mode path the benchmark configs run.
+// k_render_pool — fixed spp, default mode.  Warp-persistent: every warp pulls (8x4 pixel block,
+// sample chunk) items from the global queue on its own; no CTA-wide barrier after scene staging.
 // =========================================================================================
-template <int KIND, bool FULL>
-__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_mega(const DevScene S, const RenderParams R) {
+// POOL = true : the (pixel, sample) pairs of the item are one pool shared by the 32 lanes (best when
+//               pixels of a block cost very different amounts: BVH scenes, sky next to geometry).
+// POOL = false: lane k keeps pixel k and walks its samples in order with register accumulators
+//               (best when neighbouring pixels cost about the same: the shared-memory reductions and
+//               the queue arithmetic are not worth their ~5 %).
+// Both give bit-identical images (exact fixed-point sums).
+template <int KIND, bool POOL>
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevScene S, const RenderParams R) {
   __shared__ ListSmem sm;
+  // per warp: 32 pixels x (r, g, b) x three 21-bit limbs of the fixed-point sums.  A limb accumulator
+  // absorbs 2048 additions before it can overflow, so the adds need no carry and no return value:
+  // they are fire-and-forget shared-memory reductions.
+  __shared__ unsigned int s_acc[8][32 * 9];
   const SmemList L = stage_list<KIND>(S, sm);
   const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const int chunks = R.chunks;
+  const int blocks_x = R.tiles_x * 2, blocks_y = R.tiles_y * 4; // 8x4 pixel blocks covering the tile grid
+  const int n_items = blocks_x * blocks_y * chunks;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned int* acc = s_acc[threadIdx.x >> 5];
 
-  const int tx = (R.x0 / kTile) + blockIdx.x, ty = (R.y0 / kTile) + blockIdx.y;
-  const bool owned = R.part_count <= 1 || ((tx + ty) % R.part_count) == R.part_index;
-  int lx, ly;
-  tile_pixel(lx, ly);
-  const int i = tx * kTile + lx, j = ty * kTile + ly;
-  const bool active = owned && i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
-  const uint32_t pixel = (uint32_t)j * (uint32_t)cam.width + (uint32_t)i;
+  // RenderStats partials of this lane over all items of its warp
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  int st_bmin = 0x7fffffff, st_bmax = 0;
 
-  // PixelStats (renderStats.ts:67-88)
-  V3 color = mk3(0, 0, 0);
-  int samples = 0;
-  unsigned int bounces_sum = 0, rays = 0; // per pixel: < 2^32 for any sane spp * depth
-  int min_b = 0x7fffffff, max_b = 0;
-  double sum_ill = 0, sum_ill2 = 0;
-  float m2x = 0, m2y = 0, m2z = 0; // sum of squares for the optional moments output
-
-  // path state
-  Ray ray{mk3(0, 0, 0), mk3(0, 0, 1)};
-  V3 tp = mk3(1, 1, 1), radiance = mk3(0, 0, 0);
-  int bounces = 0;
-  bool need_path = true;
-  Rng g;
-  const int nl = S.n_lights;
-  const float wl = nl > 0 ? 0.5f / (float)nl : 0.f;
-  float total_w = 0.5f; // MixturePDF totalWeight: 0.5 + n * (0.5/n), summed like pdf.ts:71
-  for (int k = 0; k < nl; ++k) total_w += wl;
-  const float inv_total_w = 1.0f / total_w;
-
-  while (active) {
-    if (need_path) {
-      // while (pixel.samples < samples && !pixelConverged(pixel)) — camera.ts:406
-      bool stop = samples >= cam.samples;
-      if (FULL && !stop && cam.adaptive && samples >= 2 && (samples % cam.a_batch) == 0) { // camera.ts:348-368
-        double n = (double)samples;
-        double mean = sum_ill / n;
-        double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
-        if (var <= 0.0 || var != var) stop = true;
-        else stop = 1.96 * sqrt(var) / sqrt(n) <= (double)cam.a_tol * mean;
-      }
-      if (stop) break;
-      tp = mk3(1, 1, 1);
-      radiance = mk3(0, 0, 0);
-      bounces = 0;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(R.queue, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
+    const int blk = item / chunks, chunk = item - blk * chunks;
+    const int bx = blk % blocks_x, by = blk / blocks_x;
+    const int tx = (R.x0 / kTile) + (bx >> 1), ty = (R.y0 / kTile) + (by >> 2);
+    if (R.part_count > 1 && ((tx + ty) % R.part_count) != R.part_index) continue; // another GPU's tile
+    const int px0 = (R.x0 / kTile) * kTile + bx * 8, py0 = (R.y0 / kTile) * kTile + by * 4;
+    if (px0 >= R.x1 || py0 >= R.y1 || px0 + 8 <= R.x0 || py0 + 4 <= R.y0) continue; // block entirely outside the region
+    const int s_begin = (int)(((long long)cam.samples * chunk) / chunks);
+    const int s_end = (int)(((long long)cam.samples * (chunk + 1)) / chunks);
+    const int pool = 32 * (s_end - s_begin); // (pixel, sample) pairs of this item
+    if (POOL) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[lane * 9 + k] = 0;
+      __syncwarp();
     }
-    // one Philox block per bounce, generated by all lanes together
-    g.begin(pixel, (uint32_t)samples, (uint32_t)bounces, S.seed_lo, S.seed_hi);
-    if (need_path) {
-      ray = camera_ray(cam, i, j, g, true);
-      need_path = false;
-    }
-    // ---- one rayColor call (camera.ts:221-319) ----
-    bool done = bounces >= cam.depth;
-    if (!done && cam.roulette && bounces >= cam.rr_depth) { // camera.ts:233-245
-      float p = fminf(maxc(tp), 0.95f);
-      done = g.next() > p;
-      tp = tp * (1.0f / p);
-    }
-    if (!done) {
-      float t;
-      int slot;
-      ++rays;
-      if (!closest_hit<KIND>(S, L, ray, t, slot)) { // camera.ts:252-258
-        V3 ud = normalize3(ray.d);
-        float a = 0.5f * (ud.y + 1.0f);
-        V3 bg = ld3(cam.bg_top) * (1.0f - a) + ld3(cam.bg_bottom) * a;
-        radiance = radiance + bg * tp;
-        done = true;
-      } else {
-        int type, root;
-        F4 p0;
-        if (KIND == BVH_LIST) { type = sm.type[slot]; root = sm.mat[slot]; p0 = sm.p0[slot]; }
-        else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
-        const Surf sf = surface_at(type, p0, ray, t);
-        const I4 mb = ldgi4(S.matB + root);
-        const F4 ma = ldg4(S.matA + root);
-        if (mb.w) { // emitted * throughput (camera.ts:261)
-          F4 e = ldg4(S.matE + root);
-          radiance = radiance + xyz(e) * tp;
-        }
-        Scatter sc;
-        if (mb.x == MAT_LAMBERT) { sc.kind = SCATTER_DIFFUSE; sc.attenuation = xyz(ma); sc.dir = mk3(0, 0, 0); }
-        else if (mb.x == MAT_LIGHT) { sc.kind = SCATTER_NONE; sc.attenuation = mk3(0, 0, 0); sc.dir = mk3(0, 0, 0); }
-        else sc = scatter_material(S, root, mb, ma, ray.d, sf, g);
-        if (sc.kind == SCATTER_NONE) done = true; // camera.ts:267-269 (bounce not counted)
-        else {
-          ++bounces;
-          if (sc.kind == SCATTER_SPECULAR) { // camera.ts:275-282
-            tp = tp * sc.attenuation;
-            ray = Ray{sf.p, sc.dir};
-          } else { // camera.ts:285-315 with MixturePDF([cosine, lights...], [0.5, 0.5/n ...]) — pdf.ts:57-99
-            const Onb onb = make_onb(sf.n);
-            const float rnd = g.next() * total_w;
-            const float r1 = g.next(), r2 = g.next();
-            V3 dir = onb_local(onb, cosine_direction(r1, r2));
-            if (nl > 0) {
-              float partial = 0.5f;
-              int chosen = nl - 1;
-              for (int k = 0; k < nl; ++k) {
-                partial += wl;
-                if (rnd < partial) { chosen = k; break; }
-              }
-              V3 ldir = light_random_vec(S.lights[chosen], sf.p, r1, r2);
-              dir = sel3(rnd < 0.5f, dir, ldir);
-            }
-            const float cz = dot3(dir, onb.w); // all three generators return unit vectors
-            const float cosv = cz <= 0.f ? 0.f : cz * 0.31830988618f;
-            float sum = 0.5f * cosv;
-            for (int k = 0; k < nl; ++k) sum = fmaf(wl, light_pdf_value(S, S.lights[k], sf.p, dir), sum);
-            const float pdf_value = sum * inv_total_w;
-            if (!(pdf_value > 0.0001f)) done = true; // camera.ts:298-301 (NaN also ends the path)
-            else {
-              tp = tp * (sc.attenuation * (cosv * rcp_approx(pdf_value)));
-              ray = Ray{sf.p, dir};
-            }
+
+    PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+    int lp = (int)lane, sample = 0;             // current pair
+    int pi_x = px0 + (int)(lane & 7u), pi_y = py0 + (int)(lane >> 3);
+    int next = POOL ? 0 : s_begin;              // POOL: warp-uniform cursor into the pool; else this lane's next sample
+    bool have = false, retired = false;
+    unsigned long long own[3] = {0, 0, 0};      // !POOL: this lane's pixel sums
+    Rng g;
+    if (!POOL) retired = !(pi_x >= R.x0 && pi_x < R.x1 && pi_y >= R.y0 && pi_y < R.y1);
+
+    for (;;) {
+      const bool want = !have && !retired;
+      bool fresh = false;
+      if (POOL) {
+        // ---- warp-level queue: lanes without a path take the next (pixel, sample) pairs in lane order ----
+        const unsigned m = __ballot_sync(0xffffffffu, want);
+        if (want) {
+          const int idx = next + __popc(m & lt_mask);
+          if (idx >= pool) retired = true;
+          else {
+            lp = idx & 31;
+            sample = s_begin + (idx >> 5);
+            pi_x = px0 + (lp & 7);
+            pi_y = py0 + (lp >> 3);
+            // pairs of pixels outside the region are dropped; the lane takes another one next round
+            fresh = pi_x >= R.x0 && pi_x < R.x1 && pi_y >= R.y0 && pi_y < R.y1;
+            have = fresh;
           }
         }
+        next += __popc(m);
+      } else if (want) {
+        if (next >= s_end) retired = true;
+        else { sample = next++; fresh = true; have = true; }
+      }
+      if (__all_sync(0xffffffffu, retired)) break;
+      if (have) {
+        const uint32_t pixel = (uint32_t)pi_y * (uint32_t)cam.width + (uint32_t)pi_x;
+        if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
+        g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
+        if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
+        if (path_step<KIND>(S, L, sm, mw, ps, g, st_rays)) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
+          const float c[3] = {ps.radiance.x, ps.radiance.y, ps.radiance.z};
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const unsigned long long v = to_fixed(c[k]); // < 2^49
+            if (POOL) {
+              const unsigned l0 = (unsigned)v & 0x1fffffu, l1 = (unsigned)(v >> 21) & 0x1fffffu, l2 = (unsigned)(v >> 42);
+              atomicAdd(&acc[lp * 9 + 3 * k], l0);
+              atomicAdd(&acc[lp * 9 + 3 * k + 1], l1);
+              if (l2) atomicAdd(&acc[lp * 9 + 3 * k + 2], l2); // radiance >= 1024: rare
+            } else {
+              own[k] += v;
+            }
+          }
+          ++st_paths;
+          st_bounces += (unsigned)ps.bounces;
+          st_bmin = min(st_bmin, ps.bounces);
+          st_bmax = max(st_bmax, ps.bounces);
+          have = false;
+        }
       }
     }
-    if (done) { // pixel.add(rayColor, bounces, useAdaptiveSampling) — renderStats.ts:76-88
-      color = color + radiance;
-      ++samples;
-      bounces_sum += (unsigned)bounces;
-      min_b = min(min_b, bounces);
-      max_b = max(max_b, bounces);
-      if (FULL) {
+    __syncwarp();
+
+    // ---- item epilogue: lane k owns pixel k of the block ----
+    const int i = px0 + (int)(lane & 7u), j = py0 + (int)(lane >> 3);
+    const bool active = i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
+    const size_t pi = (size_t)j * cam.width + i;
+    unsigned long long sum[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      sum[k] = !POOL ? own[k]
+                     : (unsigned long long)acc[lane * 9 + 3 * k] + ((unsigned long long)acc[lane * 9 + 3 * k + 1] << 21) +
+                           ((unsigned long long)acc[lane * 9 + 3 * k + 2] << 42);
+    if (chunks == 1) {
+      if (active) {
+        ++st_pixels;
+        write_pixel(R, pi, mk3(from_fixed(sum[0], cam.samples), from_fixed(sum[1], cam.samples), from_fixed(sum[2], cam.samples)));
+      }
+    } else {
+      if (active) {
+        atomicAdd(R.accum + pi * 4 + 0, sum[0]);
+        atomicAdd(R.accum + pi * 4 + 1, sum[1]);
+        atomicAdd(R.accum + pi * 4 + 2, sum[2]);
+      }
+      __threadfence();
+      __syncwarp();
+      int last = 0;
+      if (lane == 0) last = atomicAdd(R.tile_done + blk, 1) == chunks - 1;
+      last = __shfl_sync(0xffffffffu, last, 0);
+      if (last) { // this warp finished the block's last chunk: every partial sum is in `accum`
+        __threadfence();
+        if (active) {
+          ++st_pixels;
+          const unsigned long long* a = R.accum + pi * 4;
+          write_pixel(R, pi, mk3(from_fixed(__ldcg(a), cam.samples), from_fixed(__ldcg(a + 1), cam.samples), from_fixed(__ldcg(a + 2), cam.samples)));
+        }
+      }
+    }
+    __syncwarp(); // acc is cleared at the top of the next item
+  }
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+}
+
+// =========================================================================================
+// k_render_pixels — adaptive sampling, render modes, moments: one thread = one pixel, samples in order
+// =========================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pixels(const DevScene S, const RenderParams R) {
+  __shared__ ListSmem sm;
+  __shared__ int s_item;
+  const SmemList L = stage_list<KIND>(S, sm);
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  int lx, ly;
+  tile_pixel(threadIdx.x, lx, ly);
+  const int n_items = R.tiles_x * R.tiles_y;
+
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_item = atomicAdd(R.queue, 1);
+    __syncthreads();
+    const int tile = s_item;
+    if (tile >= n_items) break;
+    const int tx = (R.x0 / kTile) + tile % R.tiles_x, ty = (R.y0 / kTile) + tile / R.tiles_x;
+    if (R.part_count > 1 && ((tx + ty) % R.part_count) != R.part_index) continue;
+    const int i = tx * kTile + lx, j = ty * kTile + ly;
+    const bool active = i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
+    const uint32_t pixel = (uint32_t)j * (uint32_t)cam.width + (uint32_t)i;
+
+    // PixelStats (renderStats.ts:67-88)
+    V3 color = mk3(0, 0, 0);
+    int samples = 0;
+    unsigned int bounces_sum = 0, rays = 0;
+    int min_b = 0x7fffffff, max_b = 0;
+    double sum_ill = 0, sum_ill2 = 0;
+    float m2x = 0, m2y = 0, m2z = 0;
+    PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+    bool need_path = true;
+    Rng g;
+
+    while (active) {
+      if (need_path) {
+        // while (pixel.samples < samples && !pixelConverged(pixel)) — camera.ts:406
+        bool stop = samples >= cam.samples;
+        if (!stop && cam.adaptive && samples >= 2 && (samples % cam.a_batch) == 0) { // camera.ts:348-368
+          double n = (double)samples;
+          double mean = sum_ill / n;
+          double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
+          if (var <= 0.0 || var != var) stop = true;
+          else stop = 1.96 * sqrt(var) / sqrt(n) <= (double)cam.a_tol * mean;
+        }
+        if (stop) break;
+        ps.tp = mk3(1, 1, 1);
+        ps.radiance = mk3(0, 0, 0);
+        ps.bounces = 0;
+      }
+      g.begin(pixel, (uint32_t)samples, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi);
+      if (need_path) {
+        ps.ray = camera_ray(cam, i, j, g, true);
+        need_path = false;
+      }
+      if (path_step<KIND>(S, L, sm, mw, ps, g, rays)) { // pixel.add(rayColor, bounces, useAdaptiveSampling)
+        color = color + ps.radiance;
+        ++samples;
+        bounces_sum += (unsigned)ps.bounces;
+        min_b = min(min_b, ps.bounces);
+        max_b = max(max_b, ps.bounces);
         if (cam.adaptive) {
-          double il = 0.299 * (double)radiance.x + 0.587 * (double)radiance.y + 0.114 * (double)radiance.z;
+          double il = 0.299 * (double)ps.radiance.x + 0.587 * (double)ps.radiance.y + 0.114 * (double)ps.radiance.z;
           sum_ill += il;
           sum_ill2 += il * il;
         }
         if (R.moments) {
-          m2x = fmaf(radiance.x, radiance.x, m2x);
-          m2y = fmaf(radiance.y, radiance.y, m2y);
-          m2z = fmaf(radiance.z, radiance.z, m2z);
+          m2x = fmaf(ps.radiance.x, ps.radiance.x, m2x);
+          m2y = fmaf(ps.radiance.y, ps.radiance.y, m2y);
+          m2z = fmaf(ps.radiance.z, ps.radiance.z, m2z);
         }
-      }
-      need_path = true;
-    }
-  }
-
-  if (active) {
-    // finalColor (camera.ts:326-340) + writeColorToBuffer (camera.ts:455-472)
-    V3 fc;
-    if (FULL && cam.mode == 1) {
-      float avg = samples > 0 ? (float)((double)bounces_sum / (double)samples) : 0.f;
-      fc = mk3(0, 0, fminf(avg / (float)cam.depth, 1.0f));
-    } else if (FULL && cam.mode == 2) {
-      fc = mk3(fminf((float)samples / (float)cam.samples, 1.0f), 0, 0);
-    } else {
-      float inv = (float)(1.0 / (double)samples);
-      fc = color * inv;
-    }
-    const size_t pi = (size_t)j * cam.width + i;
-    if (R.rgb8) {
-      const float c[3] = {fc.x, fc.y, fc.z};
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        double v = floor(255.999 * sqrt((double)c[k]));
-        // Uint8ClampedArray store: NaN/negative -> 0, >255 -> 255
-        R.rgb8[pi * 3 + k] = !(v > 0.0) ? 0 : (v >= 255.0 ? 255 : (uint8_t)v);
+        need_path = true;
       }
     }
-    if (R.linear) { R.linear[pi * 3] = fc.x; R.linear[pi * 3 + 1] = fc.y; R.linear[pi * 3 + 2] = fc.z; }
-    if (FULL && R.moments) {
-      float* m = R.moments + pi * 8;
-      m[0] = color.x; m[1] = color.y; m[2] = color.z; m[3] = m2x; m[4] = m2y; m[5] = m2z;
-      m[6] = (float)samples; m[7] = (float)bounces_sum;
-    }
-  }
 
-  // RenderStats.addPixel (renderStats.ts:21-35), reduced per warp then one atomic each
-  if (R.stats) {
-    unsigned long long px = warp_sum(active ? 1ull : 0ull);
-    unsigned long long ss = warp_sum(active ? (unsigned long long)samples : 0ull);
-    unsigned long long bs = warp_sum(active ? (unsigned long long)bounces_sum : 0ull);
-    unsigned long long rs = warp_sum(active ? (unsigned long long)rays : 0ull);
-    int smin = warp_min(active ? samples : 0x7fffffff), smax = warp_max(active ? samples : 0);
-    int bmin = warp_min(active ? min_b : 0x7fffffff), bmax = warp_max(active ? max_b : 0);
-    if ((threadIdx.x & 31) == 0 && px) {
-      atomicAdd(R.stats + kStatPixels, px);
-      atomicAdd(R.stats + kStatSamples, ss);
-      atomicAdd(R.stats + kStatBounces, bs);
-      atomicAdd(R.stats + kStatRays, rs);
-      atomicMin(R.stats + kStatSamplesMin, (unsigned long long)smin);
-      atomicMax(R.stats + kStatSamplesMax, (unsigned long long)smax);
-      atomicMin(R.stats + kStatBouncesMin, (unsigned long long)bmin);
-      atomicMax(R.stats + kStatBouncesMax, (unsigned long long)bmax);
+    if (active) {
+      V3 fc; // finalColor (camera.ts:326-340)
+      if (cam.mode == 1) {
+        float avg = samples > 0 ? (float)((double)bounces_sum / (double)samples) : 0.f;
+        fc = mk3(0, 0, fminf(avg / (float)cam.depth, 1.0f));
+      } else if (cam.mode == 2) {
+        fc = mk3(fminf((float)samples / (float)cam.samples, 1.0f), 0, 0);
+      } else {
+        fc = color * (float)(1.0 / (double)samples);
+      }
+      const size_t pi = (size_t)j * cam.width + i;
+      write_pixel(R, pi, fc);
+      if (R.moments) {
+        float* m = R.moments + pi * 8;
+        m[0] = color.x; m[1] = color.y; m[2] = color.z; m[3] = m2x; m[4] = m2y; m[5] = m2z;
+        m[6] = (float)samples; m[7] = (float)bounces_sum;
+      }
     }
+    flush_stats(R, active ? 1u : 0u, samples, active ? (unsigned)samples : 0u, bounces_sum, rays, min_b, max_b);
   }
 }
 
@@ -290,7 +491,7 @@ __global__ void __launch_bounds__(256) k_trace_primary(const DevScene S, const R
   const SmemList L = stage_list<KIND>(S, sm);
   const int tx = (R.x0 / kTile) + blockIdx.x, ty = (R.y0 / kTile) + blockIdx.y;
   int lx, ly;
-  tile_pixel(lx, ly);
+  tile_pixel(threadIdx.x, lx, ly);
   const int i = tx * kTile + lx, j = ty * kTile + ly;
   if (!(i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1)) return;
   Rng g{};
@@ -330,35 +531,59 @@ __global__ void __launch_bounds__(256) k_fp32_peak(float* out, int iters, float 
 // =========================================================================================
 // launchers (called from rt_api.cu)
 // =========================================================================================
-static dim3 tile_grid(const RenderParams& R) {
+void render_tile_grid(const RenderParams& R, int* tiles_x, int* tiles_y) {
   int tx0 = R.x0 / kTile, ty0 = R.y0 / kTile;
   int tx1 = (R.x1 - 1) / kTile, ty1 = (R.y1 - 1) / kTile;
-  return dim3((unsigned)(tx1 - tx0 + 1), (unsigned)(ty1 - ty0 + 1), 1);
+  *tiles_x = tx1 - tx0 + 1;
+  *tiles_y = ty1 - ty0 + 1;
 }
 
-template <bool FULL>
-static void launch_mega_kind(const DevScene& S, const RenderParams& R, dim3 grid, cudaStream_t st) {
-  dim3 block(256);
-  switch (S.bvh_kind) {
-    case BVH_LIST: k_render_mega<BVH_LIST, FULL><<<grid, block, 0, st>>>(S, R); break;
-    case BVH_SAH: k_render_mega<BVH_SAH, FULL><<<grid, block, 0, st>>>(S, R); break;
-    default: k_render_mega<BVH_REFERENCE, FULL><<<grid, block, 0, st>>>(S, R); break;
-  }
+bool render_needs_full(const DevScene& S, const RenderParams& R) {
+  static const bool force = getenv("RT_B200_FORCE_PIXELS") != nullptr; // development switch
+  return force || S.cam.adaptive || S.cam.mode != 0 || R.moments != nullptr;
 }
 
-cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, cudaStream_t st) {
-  if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
-  dim3 grid = tile_grid(R);
-  const bool full = S.cam.adaptive || S.cam.mode != 0 || R.moments != nullptr;
-  if (full) launch_mega_kind<true>(S, R, grid, st);
-  else launch_mega_kind<false>(S, R, grid, st);
+template <class K>
+static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderParams& R, long long items, int sms, cudaStream_t st) {
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long resident = (long long)sms * per_sm;
+  int grid = (int)(items < resident ? items : resident);
+  if (grid < 1) grid = 1;
+  kernel<<<grid, 256, 0, st>>>(S, R);
   return cudaGetLastError();
+}
+
+cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st) {
+  if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
+  const long long tiles = (long long)R.tiles_x * R.tiles_y;
+  if (render_needs_full(S, R)) {
+    switch (S.bvh_kind) {
+      case BVH_LIST: return launch_persistent(k_render_pixels<BVH_LIST>, S, R, tiles, sms, st);
+      case BVH_SAH: return launch_persistent(k_render_pixels<BVH_SAH>, S, R, tiles, sms, st);
+      default: return launch_persistent(k_render_pixels<BVH_REFERENCE>, S, R, tiles, sms, st);
+    }
+  }
+  switch (S.bvh_kind) {
+    // a tile = 8 warp blocks; a CTA runs 8 warps => one CTA per `tiles * chunks` warp items at most
+    case BVH_LIST: {
+      static const bool pool_list = getenv("RT_B200_POOL_LIST") != nullptr; // development switch
+      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, tiles * R.chunks, sms, st);
+      return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, tiles * R.chunks, sms, st);
+    }
+    case BVH_SAH: return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, tiles * R.chunks, sms, st);
+    default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, tiles * R.chunks, sms, st);
+  }
 }
 
 cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* obj_id, float* t, float* normal,
                                  uint8_t* front, cudaStream_t st) {
   if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
-  dim3 grid = tile_grid(R), block(256);
+  int gx, gy;
+  render_tile_grid(R, &gx, &gy);
+  dim3 grid((unsigned)gx, (unsigned)gy, 1), block(256);
   switch (S.bvh_kind) {
     case BVH_LIST: k_trace_primary<BVH_LIST><<<grid, block, 0, st>>>(S, R, obj_id, t, normal, front); break;
     case BVH_SAH: k_trace_primary<BVH_SAH><<<grid, block, 0, st>>>(S, R, obj_id, t, normal, front); break;

@@ -108,6 +108,16 @@ struct RenderParams {
   float* linear;               // [H][W][3] or null
   float* moments;              // [H][W][8] or null
   unsigned long long* stats;   // device RenderStats accumulator (see kStat*)
+  // Work decomposition of the render kernels: work item = (tile, sample chunk).  A pixel's samples
+  // are cut into `chunks` contiguous ranges that different CTAs may run.  Radiance sums are kept in
+  // 64-bit fixed point (2^-32 units), so adding them is exact and order-independent: the image is
+  // bit-identical whatever the chunking, the scheduling or the number of GPUs.  Partial sums of a
+  // chunk go to `accum` [H][W][4] with atomics; the CTA that finishes a tile last writes its pixels.
+  int tiles_x, tiles_y;        // tile grid covering the region
+  int chunks;
+  unsigned long long* accum;   // [H][W][4] (r, g, b, unused), zero before the launch; chunks > 1 only
+  int* queue;                  // [0] = next work item
+  int* tile_done;              // [tiles_x * tiles_y] finished chunks per tile
 };
 enum : int {
   kStatPixels = 0, kStatSamples, kStatBounces, kStatRays,
