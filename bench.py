@@ -159,6 +159,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there)
+    # are sent to stderr for the duration of the run.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +204,7 @@ def main():
             "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------- B200 arm
@@ -365,7 +373,7 @@ def main():
         "gpu_launches": kernel_launches_per_step * args.steps * world,
         "roofline": roof, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
     cam.close()
     if world > 1:
         dist.destroy_process_group()
