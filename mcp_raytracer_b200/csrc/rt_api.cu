@@ -187,6 +187,7 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   d.n_lights = (int)c->hs.lights.size();
   d.bvh_kind = c->hs.bvh_kind;
   d.planar_any = c->hs.planar_any;
+  for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs.list_n[k];
   d.seed_lo = (uint32_t)opts->seed;
   d.seed_hi = (uint32_t)(opts->seed >> 32);
   if (cudaMalloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
@@ -280,6 +281,10 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       // only the rows of the region are touched
       const size_t row = (size_t)4 * c->hs.image_width;
       CU(cudaMemsetAsync(c->d_scratch + row * P.y0, 0, row * (size_t)(P.y1 - P.y0) * sizeof(unsigned long long), c->stream));
+    }
+    {
+      static const int trav_env = getenv("RT_B200_TRAV_MIN") ? atoi(getenv("RT_B200_TRAV_MIN")) : -1; // development override
+      P.trav_min_lanes = trav_env >= 0 ? trav_env : 12;
     }
     P.queue = c->d_queue;
     P.tile_done = c->d_queue + 1;

@@ -1,23 +1,25 @@
 // rt_megakernel.cu — register-resident path tracer ("megakernel" integrator) and the
 // primary-visibility parity kernel, for sm_100a.
 //
-// Work decomposition (both render kernels): the image region is cut into 16x16 tiles and every
-// pixel's samples into `chunks` contiguous ranges; a work item is (tile, chunk).  The grid is
-// persistent (resident CTAs only); each CTA pulls items from an atomic queue, so the tail of a render
-// is one item long instead of one wave long, and a GPU that owns only 1/8 of the tiles still fills its
-// SMs evenly.
+// Work decomposition (all render kernels): persistent grid (resident CTAs only) pulling work items
+// from an atomic queue, so the tail of a render is one item long instead of one wave long, and a GPU
+// that owns only 1/8 of the tiles still fills its SMs evenly.
 //
-// k_render_pool (fixed spp, default mode — the benchmark path): inside an item the 256 x chunk
-// (pixel, sample) pairs form a pool; lanes fetch the next pair with a warp-aggregated atomic (ballot +
-// popc prefix, one shared-memory atomic per warp per fetch) whenever their path ends, so every
-// iteration every lane generates one Philox block, traces exactly one ray and shades one hit — no lane
-// waits for a neighbour's longer path or cheaper pixel.  Radiance is accumulated per pixel in 64-bit
-// fixed point (shared-memory atomics), which is exact and order-independent: the image does not depend
-// on which lane took which sample, on the chunking or on the number of GPUs.
+// k_render_pool<KIND, POOL> and k_render_trav (fixed spp, default mode — the benchmark path) are
+// warp-persistent: a work item is (8x4 pixel block, sample chunk) and belongs to ONE warp; there is no
+// CTA-wide barrier after scene staging.  Lanes take (pixel, sample) pairs from a warp-level queue
+// (ballot + popc prefix over a warp-uniform cursor) whenever their path ends, so every iteration every
+// lane generates one Philox block, traces one ray and shades one hit.  Radiance is accumulated per
+// pixel in exact 64-bit fixed point, so the image does not depend on which lane took which sample, on
+// the chunking or on the number of GPUs.
+//   * k_render_pool<LIST>: tiny scenes, all primitives in shared memory, converged brute-force loop.
+//   * k_render_trav (SAH trees): BVH traversal is a resumable state machine; a warp alternates
+//     between traversal steps (one node visit for every lane that is mid-ray) and shading/regeneration
+//     for the lanes whose ray finished, switching when too few lanes still traverse — the warp never
+//     waits for its longest traversal with idle lanes.
 //
 // k_render_pixels (adaptive sampling / render modes / moments): one thread owns one pixel and runs the
-// reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule requires, with
-// the same per-lane path regeneration.
+// reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule requires.
 //
 // All path state lives in registers; HBM sees the scene reads (L1/L2 resident), 24 B of atomics per
 // (pixel, chunk) when chunks > 1, and 3 bytes per pixel of output.
@@ -29,6 +31,9 @@ static constexpr int kTile = 16;
 static constexpr int kListMax = 64;
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 2
+#endif
+#ifndef RT_TRAV_MIN_LANES
+#define RT_TRAV_MIN_LANES 20 // leave the traversal phase when this many lanes or fewer still traverse
 #endif
 
 RT_DEV unsigned long long warp_sum(unsigned long long v) {
@@ -70,7 +75,9 @@ RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
       sm.p2[s] = ldg4(S.p2 + s);
       sm.p3[s] = ldg4(S.p3 + s);
       I2 info = ldgi2(S.slot_info + s);
-      sm.type[s] = (info.y >> 30) & 3;
+      const int ty = (info.y >> 30) & 3;
+      // axis-aligned quads get one warp-uniform code per axis so the converged loop never selects components
+      sm.type[s] = ty == OBJ_AAQUAD ? OBJ_AAQUAD + 1 + __float_as_int(sm.p2[s].y) : ty;
       sm.mat[s] = info.x;
     }
     __syncthreads();
@@ -81,7 +88,7 @@ RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
 
 template <int KIND>
 RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
-  RayPre pre = precompute(r, KIND != BVH_LIST);
+  RayPre pre = precompute(r, true); // LIST uses idir too (axis-aligned quads); unused parts are dead code
   t = CUDART_INF_F;
   slot = -1;
   if (KIND == BVH_LIST) trace_list(S, L, r, pre, t, slot);
@@ -111,23 +118,23 @@ struct PathState {
   int bounces;
 };
 
-// One rayColor call (camera.ts:221-319) on the path's current ray.  Returns true when the path ended
-// (its radiance is complete); otherwise ps.ray / ps.tp / ps.bounces describe the next call.
-template <int KIND>
-RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
-                      unsigned& rays) {
-  const DevCamera& cam = S.cam;
+// rayColor, part 1 (camera.ts:228-245): depth limit and Russian roulette.  True = the path ended.
+RT_DEV bool path_pre(const DevCamera& cam, PathState& ps, Rng& g) {
   bool done = ps.bounces >= cam.depth;
-  if (!done && cam.roulette && ps.bounces >= cam.rr_depth) { // camera.ts:233-245
+  if (!done && cam.roulette && ps.bounces >= cam.rr_depth) {
     float p = fminf(maxc(ps.tp), 0.95f);
     done = g.next() > p;
     ps.tp = ps.tp * rcp_approx(p);
   }
-  if (done) return true;
-  float t;
-  int slot;
-  ++rays;
-  if (!closest_hit<KIND>(S, L, ps.ray, t, slot)) { // camera.ts:252-258
+  return done;
+}
+
+// rayColor, part 2 (camera.ts:249-319) given the closest hit (slot < 0: miss).  True = the path ended
+// (its radiance is complete); otherwise ps.ray / ps.tp / ps.bounces describe the next call.
+template <int KIND>
+RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t, int slot) {
+  const DevCamera& cam = S.cam;
+  if (slot < 0) { // camera.ts:252-258
     V3 ud = normalize3(ps.ray.d);
     float a = 0.5f * (ud.y + 1.0f);
     V3 bg = ld3(cam.bg_top) * (1.0f - a) + ld3(cam.bg_bottom) * a;
@@ -136,7 +143,7 @@ RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, 
   }
   int type, root;
   F4 p0;
-  if (KIND == BVH_LIST) { type = sm.type[slot]; root = sm.mat[slot]; p0 = sm.p0[slot]; }
+  if (KIND == BVH_LIST) { type = sm->type[slot]; root = sm->mat[slot]; p0 = sm->p0[slot]; }
   else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
   const Surf sf = surface_at(type, p0, ps.ray, t);
   const I4 mb = ldgi4(S.matB + root);
@@ -180,6 +187,18 @@ RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, 
   ps.tp = ps.tp * (sc.attenuation * (cosv * rcp_approx(pdf_value)));
   ps.ray = Ray{sf.p, dir};
   return false;
+}
+
+// One whole rayColor call on the path's current ray.
+template <int KIND>
+RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
+                      unsigned& rays) {
+  if (path_pre(S.cam, ps, g)) return true;
+  float t;
+  int slot;
+  ++rays;
+  closest_hit<KIND>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
+  return path_post<KIND>(S, &sm, mw, ps, g, t, slot);
 }
 
 // finalColor (camera.ts:326-340, default mode) + writeColorToBuffer (camera.ts:455-472)
@@ -227,63 +246,132 @@ RT_DEV unsigned long long to_fixed(float x) {
 }
 RT_DEV float from_fixed(unsigned long long s, int samples) { return (float)(((double)s * (1.0 / 4294967296.0)) / (double)samples); }
 
+// ---------------------------------------------------------------------------------------------------
+// Warp-level work items: (8x4 pixel block, sample chunk)
+// ---------------------------------------------------------------------------------------------------
+struct WarpItem {
+  int blk, px0, py0, s_begin, s_end;
+};
+// Pops items until one belongs to this GPU and touches the region.  False = queue exhausted.
+RT_DEV bool next_warp_item(const RenderParams& R, int samples, unsigned lane, WarpItem& it) {
+  const int chunks = R.chunks;
+  const int blocks_x = R.tiles_x * 2, blocks_y = R.tiles_y * 4; // 8x4 blocks covering the tile grid
+  const int n_items = blocks_x * blocks_y * chunks;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(R.queue, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) return false;
+    const int blk = item / chunks, chunk = item - blk * chunks;
+    const int bx = blk % blocks_x, by = blk / blocks_x;
+    const int tx = (R.x0 / kTile) + (bx >> 1), ty = (R.y0 / kTile) + (by >> 2);
+    if (R.part_count > 1 && ((tx + ty) % R.part_count) != R.part_index) continue; // another GPU's tile
+    it.px0 = (R.x0 / kTile) * kTile + bx * 8;
+    it.py0 = (R.y0 / kTile) * kTile + by * 4;
+    if (it.px0 >= R.x1 || it.py0 >= R.y1 || it.px0 + 8 <= R.x0 || it.py0 + 4 <= R.y0) continue; // block outside the region
+    it.blk = blk;
+    it.s_begin = (int)(((long long)samples * chunk) / chunks);
+    it.s_end = (int)(((long long)samples * (chunk + 1)) / chunks);
+    return true;
+  }
+}
+
+// Per-warp pixel accumulators: 32 pixels x (r, g, b) x three 21-bit limbs of the fixed-point sums.  A limb
+// accumulator absorbs 2048 additions before it can overflow, so the adds need no carry and no return
+// value: they are fire-and-forget shared-memory reductions.
+RT_DEV void acc_clear(unsigned int* acc, unsigned lane) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[lane * 9 + k] = 0;
+  __syncwarp();
+}
+RT_DEV void acc_add(unsigned int* acc, int lp, V3 radiance) {
+  const float c[3] = {radiance.x, radiance.y, radiance.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned long long v = to_fixed(c[k]); // < 2^49
+    const unsigned l0 = (unsigned)v & 0x1fffffu, l1 = (unsigned)(v >> 21) & 0x1fffffu, l2 = (unsigned)(v >> 42);
+    atomicAdd(&acc[lp * 9 + 3 * k], l0);
+    atomicAdd(&acc[lp * 9 + 3 * k + 1], l1);
+    if (l2) atomicAdd(&acc[lp * 9 + 3 * k + 2], l2); // radiance >= 1024: rare
+  }
+}
+RT_DEV void acc_read(const unsigned int* acc, unsigned lane, unsigned long long sum[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    sum[k] = (unsigned long long)acc[lane * 9 + 3 * k] + ((unsigned long long)acc[lane * 9 + 3 * k + 1] << 21) +
+             ((unsigned long long)acc[lane * 9 + 3 * k + 2] << 42);
+}
+
+// Item epilogue: lane k owns pixel k of the block.  chunks == 1: write the pixel.  Otherwise add the
+// chunk's sums to `accum` and let the warp that completes the block's last chunk write it.
+// Returns 1 when this lane wrote its pixel.
+RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const WarpItem& it, unsigned lane, const unsigned long long sum[3]) {
+  const int i = it.px0 + (int)(lane & 7u), j = it.py0 + (int)(lane >> 3);
+  const bool active = i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
+  const size_t pi = (size_t)j * cam.width + i;
+  unsigned wrote = 0;
+  if (R.chunks == 1) {
+    if (active) {
+      wrote = 1;
+      write_pixel(R, pi, mk3(from_fixed(sum[0], cam.samples), from_fixed(sum[1], cam.samples), from_fixed(sum[2], cam.samples)));
+    }
+  } else {
+    if (active) {
+      atomicAdd(R.accum + pi * 4 + 0, sum[0]);
+      atomicAdd(R.accum + pi * 4 + 1, sum[1]);
+      atomicAdd(R.accum + pi * 4 + 2, sum[2]);
+    }
+    __threadfence();
+    __syncwarp();
+    int last = 0;
+    if (lane == 0) last = atomicAdd(R.tile_done + it.blk, 1) == R.chunks - 1;
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) { // every partial sum of the block is in `accum`
+      __threadfence();
+      if (active) {
+        wrote = 1;
+        const unsigned long long* a = R.accum + pi * 4;
+        write_pixel(R, pi, mk3(from_fixed(__ldcg(a), cam.samples), from_fixed(__ldcg(a + 1), cam.samples), from_fixed(__ldcg(a + 2), cam.samples)));
+      }
+    }
+  }
+  return wrote;
+}
+
 // =========================================================================================
-// k_render_pool — fixed spp, default mode.  Warp-persistent: every warp pulls (8x4 pixel block,
-// sample chunk) items from the global queue on its own; no CTA-wide barrier after scene staging.
-// =========================================================================================
-// POOL = true : the (pixel, sample) pairs of the item are one pool shared by the 32 lanes (best when
-//               pixels of a block cost very different amounts: BVH scenes, sky next to geometry).
+// k_render_pool — fixed spp, default mode, whole closest-hit query per iteration.
+// POOL = true : the (pixel, sample) pairs of the item are one pool shared by the 32 lanes.
 // POOL = false: lane k keeps pixel k and walks its samples in order with register accumulators
-//               (best when neighbouring pixels cost about the same: the shared-memory reductions and
-//               the queue arithmetic are not worth their ~5 %).
+//               (neighbouring pixels cost about the same: the shared-memory reductions and the queue
+//               arithmetic are not worth their ~1-2 %).
 // Both give bit-identical images (exact fixed-point sums).
+// =========================================================================================
 template <int KIND, bool POOL>
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevScene S, const RenderParams R) {
   __shared__ ListSmem sm;
-  // per warp: 32 pixels x (r, g, b) x three 21-bit limbs of the fixed-point sums.  A limb accumulator
-  // absorbs 2048 additions before it can overflow, so the adds need no carry and no return value:
-  // they are fire-and-forget shared-memory reductions.
-  __shared__ unsigned int s_acc[8][32 * 9];
+  __shared__ unsigned int s_acc[POOL ? 8 : 1][32 * 9];
   const SmemList L = stage_list<KIND>(S, sm);
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
-  const int chunks = R.chunks;
-  const int blocks_x = R.tiles_x * 2, blocks_y = R.tiles_y * 4; // 8x4 pixel blocks covering the tile grid
-  const int n_items = blocks_x * blocks_y * chunks;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
-  unsigned int* acc = s_acc[threadIdx.x >> 5];
+  unsigned int* acc = s_acc[POOL ? (threadIdx.x >> 5) : 0];
 
   // RenderStats partials of this lane over all items of its warp
   unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(R.queue, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= n_items) break;
-    const int blk = item / chunks, chunk = item - blk * chunks;
-    const int bx = blk % blocks_x, by = blk / blocks_x;
-    const int tx = (R.x0 / kTile) + (bx >> 1), ty = (R.y0 / kTile) + (by >> 2);
-    if (R.part_count > 1 && ((tx + ty) % R.part_count) != R.part_index) continue; // another GPU's tile
-    const int px0 = (R.x0 / kTile) * kTile + bx * 8, py0 = (R.y0 / kTile) * kTile + by * 4;
-    if (px0 >= R.x1 || py0 >= R.y1 || px0 + 8 <= R.x0 || py0 + 4 <= R.y0) continue; // block entirely outside the region
-    const int s_begin = (int)(((long long)cam.samples * chunk) / chunks);
-    const int s_end = (int)(((long long)cam.samples * (chunk + 1)) / chunks);
-    const int pool = 32 * (s_end - s_begin); // (pixel, sample) pairs of this item
-    if (POOL) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[lane * 9 + k] = 0;
-      __syncwarp();
-    }
+  WarpItem it;
+  while (next_warp_item(R, cam.samples, lane, it)) {
+    const int pool = 32 * (it.s_end - it.s_begin); // (pixel, sample) pairs of this item
+    if (POOL) acc_clear(acc, lane);
 
     PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
-    int lp = (int)lane, sample = 0;             // current pair
-    int pi_x = px0 + (int)(lane & 7u), pi_y = py0 + (int)(lane >> 3);
-    int next = POOL ? 0 : s_begin;              // POOL: warp-uniform cursor into the pool; else this lane's next sample
+    int lp = (int)lane, sample = 0; // current pair
+    int pi_x = it.px0 + (int)(lane & 7u), pi_y = it.py0 + (int)(lane >> 3);
+    int next = POOL ? 0 : it.s_begin; // POOL: warp-uniform cursor into the pool; else this lane's next sample
     bool have = false, retired = false;
-    unsigned long long own[3] = {0, 0, 0};      // !POOL: this lane's pixel sums
+    unsigned long long own[3] = {0, 0, 0}; // !POOL: this lane's pixel sums
     Rng g;
     if (!POOL) retired = !(pi_x >= R.x0 && pi_x < R.x1 && pi_y >= R.y0 && pi_y < R.y1);
 
@@ -298,9 +386,9 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevSce
           if (idx >= pool) retired = true;
           else {
             lp = idx & 31;
-            sample = s_begin + (idx >> 5);
-            pi_x = px0 + (lp & 7);
-            pi_y = py0 + (lp >> 3);
+            sample = it.s_begin + (idx >> 5);
+            pi_x = it.px0 + (lp & 7);
+            pi_y = it.py0 + (lp >> 3);
             // pairs of pixels outside the region are dropped; the lane takes another one next round
             fresh = pi_x >= R.x0 && pi_x < R.x1 && pi_y >= R.y0 && pi_y < R.y1;
             have = fresh;
@@ -308,7 +396,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevSce
         }
         next += __popc(m);
       } else if (want) {
-        if (next >= s_end) retired = true;
+        if (next >= it.s_end) retired = true;
         else { sample = next++; fresh = true; have = true; }
       }
       if (__all_sync(0xffffffffu, retired)) break;
@@ -318,19 +406,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevSce
         g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
         if (path_step<KIND>(S, L, sm, mw, ps, g, st_rays)) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
-          const float c[3] = {ps.radiance.x, ps.radiance.y, ps.radiance.z};
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const unsigned long long v = to_fixed(c[k]); // < 2^49
-            if (POOL) {
-              const unsigned l0 = (unsigned)v & 0x1fffffu, l1 = (unsigned)(v >> 21) & 0x1fffffu, l2 = (unsigned)(v >> 42);
-              atomicAdd(&acc[lp * 9 + 3 * k], l0);
-              atomicAdd(&acc[lp * 9 + 3 * k + 1], l1);
-              if (l2) atomicAdd(&acc[lp * 9 + 3 * k + 2], l2); // radiance >= 1024: rare
-            } else {
-              own[k] += v;
-            }
-          }
+          if (POOL) acc_add(acc, lp, ps.radiance);
+          else { own[0] += to_fixed(ps.radiance.x); own[1] += to_fixed(ps.radiance.y); own[2] += to_fixed(ps.radiance.z); }
           ++st_paths;
           st_bounces += (unsigned)ps.bounces;
           st_bmin = min(st_bmin, ps.bounces);
@@ -340,43 +417,115 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevSce
       }
     }
     __syncwarp();
+    unsigned long long sum[3] = {own[0], own[1], own[2]};
+    if (POOL) acc_read(acc, lane, sum);
+    st_pixels += item_epilogue(R, cam, it, lane, sum);
+    __syncwarp(); // acc is cleared at the top of the next item
+  }
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+}
 
-    // ---- item epilogue: lane k owns pixel k of the block ----
-    const int i = px0 + (int)(lane & 7u), j = py0 + (int)(lane >> 3);
-    const bool active = i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
-    const size_t pi = (size_t)j * cam.width + i;
-    unsigned long long sum[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      sum[k] = !POOL ? own[k]
-                     : (unsigned long long)acc[lane * 9 + 3 * k] + ((unsigned long long)acc[lane * 9 + 3 * k + 1] << 21) +
-                           ((unsigned long long)acc[lane * 9 + 3 * k + 2] << 42);
-    if (chunks == 1) {
-      if (active) {
-        ++st_pixels;
-        write_pixel(R, pi, mk3(from_fixed(sum[0], cam.samples), from_fixed(sum[1], cam.samples), from_fixed(sum[2], cam.samples)));
+// =========================================================================================
+// k_render_trav — fixed spp, default mode, SAH trees: traversal interleaved with shading.
+// Lane states: NONE (needs a pair) -> BEGIN (bounce not started) -> TRACE (mid-traversal) ->
+// HIT (closest hit known, not shaded) -> BEGIN | NONE.
+// =========================================================================================
+enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3 };
+
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevScene S, const RenderParams R) {
+  __shared__ unsigned int s_acc[8][32 * 9];
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  unsigned int* acc = s_acc[threadIdx.x >> 5];
+  int stack[64];
+
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  int st_bmin = 0x7fffffff, st_bmax = 0;
+
+  WarpItem it;
+  while (next_warp_item(R, cam.samples, lane, it)) {
+    const int pool = 32 * (it.s_end - it.s_begin);
+    acc_clear(acc, lane);
+
+    PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+    int lp = 0, sample = 0, pi_x = 0, pi_y = 0;
+    int next = 0;
+    int st = ST_NONE;
+    bool retired = false, fresh = false;
+    Trav tv{-1, 0, CUDART_INF_F, -1};
+    BoxPre bp{mk3(0, 0, 0), mk3(0, 0, 0)};
+    Rng g;
+
+    for (;;) {
+      // ---- warp-level queue: lanes without a path take the next (pixel, sample) pairs in lane order ----
+      const bool want = st == ST_NONE && !retired;
+      const unsigned m = __ballot_sync(0xffffffffu, want);
+      if (want) {
+        const int idx = next + __popc(m & lt_mask);
+        if (idx >= pool) retired = true;
+        else {
+          lp = idx & 31;
+          sample = it.s_begin + (idx >> 5);
+          pi_x = it.px0 + (lp & 7);
+          pi_y = it.py0 + (lp >> 3);
+          if (pi_x >= R.x0 && pi_x < R.x1 && pi_y >= R.y0 && pi_y < R.y1) { st = ST_BEGIN; fresh = true; }
+        }
       }
-    } else {
-      if (active) {
-        atomicAdd(R.accum + pi * 4 + 0, sum[0]);
-        atomicAdd(R.accum + pi * 4 + 1, sum[1]);
-        atomicAdd(R.accum + pi * 4 + 2, sum[2]);
+      next += __popc(m);
+      if (__all_sync(0xffffffffu, st == ST_NONE && retired)) break;
+
+      // ---- shading phase: finish the bounce of lanes whose ray is done, start the next bounce ----
+      if (st == ST_HIT) {
+        const bool done = path_post<BVH_SAH>(S, nullptr, mw, ps, g, tv.tbest, tv.sbest);
+        st = done ? ST_NONE : ST_BEGIN;
+        if (done) {
+          acc_add(acc, lp, ps.radiance);
+          ++st_paths;
+          st_bounces += (unsigned)ps.bounces;
+          st_bmin = min(st_bmin, ps.bounces);
+          st_bmax = max(st_bmax, ps.bounces);
+        }
       }
-      __threadfence();
-      __syncwarp();
-      int last = 0;
-      if (lane == 0) last = atomicAdd(R.tile_done + blk, 1) == chunks - 1;
-      last = __shfl_sync(0xffffffffu, last, 0);
-      if (last) { // this warp finished the block's last chunk: every partial sum is in `accum`
-        __threadfence();
-        if (active) {
-          ++st_pixels;
-          const unsigned long long* a = R.accum + pi * 4;
-          write_pixel(R, pi, mk3(from_fixed(__ldcg(a), cam.samples), from_fixed(__ldcg(a + 1), cam.samples), from_fixed(__ldcg(a + 2), cam.samples)));
+      if (st == ST_BEGIN) {
+        const uint32_t pixel = (uint32_t)pi_y * (uint32_t)cam.width + (uint32_t)pi_x;
+        if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
+        g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
+        if (fresh) { ps.ray = camera_ray(cam, pi_x, pi_y, g, true); fresh = false; }
+        if (path_pre(cam, ps, g)) { // ended by the depth limit or the roulette: nothing to trace
+          acc_add(acc, lp, ps.radiance);
+          ++st_paths;
+          st_bounces += (unsigned)ps.bounces;
+          st_bmin = min(st_bmin, ps.bounces);
+          st_bmax = max(st_bmax, ps.bounces);
+          st = ST_NONE;
+        } else {
+          ++st_rays;
+          trav_begin(S, ps.ray, tv);
+          bp = box_precompute(ps.ray);
+          st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
+        }
+      }
+
+      // ---- traversal phase: one node visit per round for every lane that is mid-ray ----
+      for (;;) {
+        const unsigned tm = __ballot_sync(0xffffffffu, st == ST_TRACE);
+        if (tm == 0) break;
+        // lanes that could do something else: shade a finished ray, start a bounce, take a new pair
+        const unsigned idle = __ballot_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired));
+        if (idle != 0 && __popc(tm) <= R.trav_min_lanes) break;
+        if (st == ST_TRACE) {
+          trav_step(S, ps.ray, bp, tv, stack);
+          if (tv.cur < 0) st = ST_HIT;
         }
       }
     }
-    __syncwarp(); // acc is cleared at the top of the next item
+    __syncwarp();
+    unsigned long long sum[3];
+    acc_read(acc, lane, sum);
+    st_pixels += item_epilogue(R, cam, it, lane, sum);
+    __syncwarp();
   }
   flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
 }
@@ -544,13 +693,13 @@ bool render_needs_full(const DevScene& S, const RenderParams& R) {
 }
 
 template <class K>
-static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderParams& R, long long items, int sms, cudaStream_t st) {
+static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderParams& R, long long ctas_of_work, int sms, cudaStream_t st) {
   int per_sm = 0;
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
   long long resident = (long long)sms * per_sm;
-  int grid = (int)(items < resident ? items : resident);
+  int grid = (int)(ctas_of_work < resident ? ctas_of_work : resident);
   if (grid < 1) grid = 1;
   kernel<<<grid, 256, 0, st>>>(S, R);
   return cudaGetLastError();
@@ -566,15 +715,18 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       default: return launch_persistent(k_render_pixels<BVH_REFERENCE>, S, R, tiles, sms, st);
     }
   }
+  // a tile = 8 warp blocks and a CTA runs 8 warps: `tiles * chunks` CTAs' worth of warp items
+  const long long work = tiles * R.chunks;
+  static const bool pool_list = getenv("RT_B200_POOL_LIST") != nullptr;   // development switches
+  static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
   switch (S.bvh_kind) {
-    // a tile = 8 warp blocks; a CTA runs 8 warps => one CTA per `tiles * chunks` warp items at most
-    case BVH_LIST: {
-      static const bool pool_list = getenv("RT_B200_POOL_LIST") != nullptr; // development switch
-      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, tiles * R.chunks, sms, st);
-      return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, tiles * R.chunks, sms, st);
-    }
-    case BVH_SAH: return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, tiles * R.chunks, sms, st);
-    default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, tiles * R.chunks, sms, st);
+    case BVH_LIST:
+      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
+      return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
+    case BVH_SAH:
+      if (no_trav) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
+      return launch_persistent(k_render_trav, S, R, work, sms, st);
+    default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);
   }
 }
 

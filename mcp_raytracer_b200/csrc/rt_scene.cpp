@@ -90,7 +90,37 @@ struct Prim {
   Box sah_box; // finite and non-inverted where possible
   bool bounded = true;
   F4 rec0{}, rec1{}, rec2{}, rec3{};
+  // axis-aligned quad specialisation (device type OBJ_AAQUAD): plane x_K = c, box test on the other two axes
+  bool aa = false;
+  F4 aa1{}, aa2{};
 };
+
+// u and v each along one (different) coordinate axis?
+void detect_axis_aligned(Prim& p) {
+  auto single_axis = [](const H3& a) {
+    int ax = -1;
+    for (int i = 0; i < 3; ++i)
+      if (a[i] != 0.f) { if (ax >= 0) return -1; ax = i; }
+    return ax;
+  };
+  const int iu = single_axis(p.u), iv = single_axis(p.v);
+  if (iu < 0 || iv < 0 || iu == iv) return;
+  const int K = 3 - iu - iv, I = (K + 1) % 3, J = (K + 2) % 3;
+  auto range = [&](int ax, float& lo, float& hi) { // the quad's extent along in-plane axis ax: q .. q+u (or q+v), FP32 like q.add(u)
+    const H3& e = ax == iu ? p.u : p.v;
+    const float a = p.q[ax], b = (float)((double)p.q[ax] + (double)e[ax]);
+    lo = std::min(a, b);
+    hi = std::max(a, b);
+  };
+  float loI, hiI, loJ, hiJ;
+  range(I, loI, hiI);
+  range(J, loJ, hiJ);
+  p.aa = true;
+  p.aa1 = F4{p.q[K], loI, loJ, hiI};
+  float axis_bits;
+  std::memcpy(&axis_bits, &K, sizeof(float));
+  p.aa2 = F4{hiJ, axis_bits, 0.f, 0.f};
+}
 
 void make_sphere(Prim& p) {
   H3 rv = map3([&](int) { return p.r; }); // Vec3.create(r,r,r), sphere.ts:26
@@ -155,6 +185,7 @@ void make_planar(Prim& p) {
   const double eps4 = 4.0 / 16777216.0; // 4 * 2^-24
   p.rec3 = F4{(float)(std::fabs(A[0]) + std::fabs(A[1]) + std::fabs(A[2])), (float)(std::fabs(B[0]) + std::fabs(B[1]) + std::fabs(B[2])),
               (float)(eps4 * std::fabs(a0)), (float)(eps4 * std::fabs(b0))};
+  if (p.type == OBJ_QUAD) detect_axis_aligned(p);
 }
 
 // ---- build tree (shared by both builders) ----
@@ -321,10 +352,11 @@ struct Flattener {
   void push_slot(int pi) {
     const Prim& p = P[pi];
     S.p0.push_back(p.rec0);
-    S.p1.push_back(p.rec1);
-    S.p2.push_back(p.rec2);
+    S.p1.push_back(p.aa ? p.aa1 : p.rec1);
+    S.p2.push_back(p.aa ? p.aa2 : p.rec2);
     S.p3.push_back(p.rec3);
-    S.slot_info.push_back(I2{p.mat, p.obj | (p.type << 30)});
+    const unsigned dev_type = p.aa ? (unsigned)OBJ_AAQUAD : (unsigned)p.type;
+    S.slot_info.push_back(I2{p.mat, (int)((unsigned)p.obj | (dev_type << 30))});
     ExactPrim e;
     std::memset(&e, 0, sizeof(e));
     put3(e.q, p.q); put3(e.u, p.u); put3(e.v, p.v); put3(e.n, p.n); put3(e.w, p.w);
@@ -497,9 +529,24 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   if (kind == BVH_LIST) {
     // Slots in the reference's visiting order; only the box tests are dropped, which cannot
     // change a nearest hit when no box is inverted.
+    // Grouped by primitive kind (spheres, axis-aligned quads per axis, general quads, planes) so the
+    // kernel runs one tight converged loop per kind; within a kind in the reference's visiting order.
+    // The order cannot change a result: a closer hit is accepted only when it is closer by more than the
+    // FP32 error bound, and anything nearer to a tie is decided in FP64 with the reference's
+    // first-visited-wins rule on the stored rank.
     std::vector<int> by_rank(n);
     for (uint32_t i = 0; i < n; ++i) by_rank[rank[i]] = (int)i;
-    for (int pi : by_rank) fl.push_slot(pi);
+    auto group_of = [&](int pi) {
+      const Prim& p = P[pi];
+      if (p.type == OBJ_SPHERE) return 0;
+      if (p.aa) { int K; std::memcpy(&K, &p.aa2.y, sizeof(int)); return 1 + K; }
+      return p.type == OBJ_QUAD ? 4 : 5;
+    };
+    for (int g = 0; g < 6; ++g) {
+      S.list_n[g] = 0;
+      for (int pi : by_rank)
+        if (group_of(pi) == g) { fl.push_slot(pi); S.list_n[g]++; }
+    }
     S.n_unbounded = (int)n; // every slot is "always tested"
   } else if (kind == BVH_REFERENCE) {
     // node 0 = super-root: the reference tests the root's own box first (bvh.ts:130)

@@ -17,6 +17,7 @@ struct HostScene {
   int bvh_kind = 0;
   int n_unbounded = 0;
   int planar_any = 0;
+  int list_n[6] = {0, 0, 0, 0, 0, 0}; // LIST: slots per kind (spheres, aa-quads x/y/z, quads, planes)
   int max_depth = 0; // deepest leaf below node 0
   std::vector<Node> nodes;
   std::vector<F4> p0, p1, p2, p3;

@@ -28,7 +28,9 @@
 
 namespace rt {
 
-enum : int { OBJ_SPHERE = 0, OBJ_PLANE = 1, OBJ_QUAD = 2 };
+// OBJ_AAQUAD is a device-side specialisation of OBJ_QUAD chosen by the scene compiler (u, v axis-aligned);
+// slot records p1/p2 then hold (c, lo_I, lo_J, hi_I), (hi_J, axis bits, -, -) instead of the general ones.
+enum : int { OBJ_SPHERE = 0, OBJ_PLANE = 1, OBJ_QUAD = 2, OBJ_AAQUAD = 3 };
 enum : int { MAT_LAMBERT = 0, MAT_METAL = 1, MAT_GLASS = 2, MAT_LIGHT = 3, MAT_MIXED = 4, MAT_LAYERED = 5 };
 enum : int { BVH_REFERENCE = 1, BVH_SAH = 2, BVH_LIST = 3 };
 
@@ -97,6 +99,7 @@ struct DevScene {
   int n_nodes, n_slots, n_unbounded, n_mats, n_lights;
   int bvh_kind;
   int planar_any; // scene has planes/quads
+  int list_n[6];  // LIST: slots per kind, in slot order: spheres, axis-aligned quads x/y/z, general quads, planes
   uint32_t seed_lo, seed_hi;
 };
 
@@ -117,7 +120,8 @@ struct RenderParams {
   int chunks;
   unsigned long long* accum;   // [H][W][4] (r, g, b, unused), zero before the launch; chunks > 1 only
   int* queue;                  // [0] = next work item
-  int* tile_done;              // [tiles_x * tiles_y] finished chunks per tile
+  int* tile_done;              // [8x4 blocks] finished chunks per block
+  int trav_min_lanes;          // k_render_trav: leave the traversal phase when <= this many lanes still traverse
 };
 enum : int {
   kStatPixels = 0, kStatSamples, kStatBounces, kStatRays,
