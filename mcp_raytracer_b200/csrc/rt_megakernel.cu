@@ -428,9 +428,10 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_pool(const DevSce
 // =========================================================================================
 // k_render_trav — fixed spp, default mode, SAH trees: traversal interleaved with shading.
 // Lane states: NONE (needs a pair) -> BEGIN (bounce not started) -> TRACE (mid-traversal) ->
-// HIT (closest hit known, not shaded) -> BEGIN | NONE.
+// LEAF (leaf children of the last node wait to be intersected) -> TRACE ... -> HIT (closest hit known,
+// not shaded) -> BEGIN | NONE.
 // =========================================================================================
-enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3 };
+enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3, ST_LEAF = 4 };
 
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevScene S, const RenderParams R) {
   __shared__ unsigned int s_acc[8][32 * 9];
@@ -455,6 +456,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
     int st = ST_NONE;
     bool retired = false, fresh = false;
     Trav tv{-1, 0, CUDART_INF_F, -1};
+    int leaf_a = 0, leaf_b = 0; // postponed leaves of a lane in ST_LEAF
     BoxPre bp{mk3(0, 0, 0), mk3(0, 0, 0)};
     Rng g;
 
@@ -508,16 +510,24 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
         }
       }
 
-      // ---- traversal phase: one node visit per round for every lane that is mid-ray ----
+      // ---- traversal phase: converged rounds of inner-node visits and of leaf intersections
+      //      (while-while with postponed leaves); each round serves the larger of the two groups ----
       for (;;) {
-        const unsigned tm = __ballot_sync(0xffffffffu, st == ST_TRACE);
-        if (tm == 0) break;
-        // lanes that could do something else: shade a finished ray, start a bounce, take a new pair
-        const unsigned idle = __ballot_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired));
-        if (idle != 0 && __popc(tm) <= R.trav_min_lanes) break;
-        if (st == ST_TRACE) {
-          trav_step(S, ps.ray, bp, tv, stack);
-          if (tv.cur < 0) st = ST_HIT;
+        const unsigned ti = __ballot_sync(0xffffffffu, st == ST_TRACE);
+        const unsigned tl = __ballot_sync(0xffffffffu, st == ST_LEAF);
+        if ((ti | tl) == 0) break;
+        if (__popc(ti | tl) <= R.trav_min_lanes) {
+          // lanes that could do something else: shade a finished ray, start a bounce, take a new pair
+          if (__any_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired))) break;
+        }
+        if (__popc(ti) >= __popc(tl)) {
+          if (st == ST_TRACE) {
+            trav_inner(S, bp, tv, stack, leaf_a, leaf_b);
+            st = leaf_a != 0 ? ST_LEAF : (tv.cur >= 0 ? ST_TRACE : ST_HIT);
+          }
+        } else if (st == ST_LEAF) {
+          trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
+          st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
     }
@@ -724,7 +734,9 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
       return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
     case BVH_SAH:
-      if (no_trav) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
+      // shallow trees: a whole traversal is a few node visits and interleaving only costs (measured on
+      // the 480-sphere and 55-object scenes); deep trees: lanes diverge by 10x in visit count and win.
+      if (no_trav || S.n_nodes < 4096) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
       return launch_persistent(k_render_trav, S, R, work, sms, st);
     default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);
   }

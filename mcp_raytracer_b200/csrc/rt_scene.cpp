@@ -352,10 +352,13 @@ struct Flattener {
   void push_slot(int pi) {
     const Prim& p = P[pi];
     S.p0.push_back(p.rec0);
-    S.p1.push_back(p.aa ? p.aa1 : p.rec1);
-    S.p2.push_back(p.aa ? p.aa2 : p.rec2);
+    // The axis-aligned specialisation pays in the LIST kernel, where the kind is warp-uniform; inside tree
+    // leaves the per-lane axis dispatch costs more than it saves (measured), so trees keep general quads.
+    const bool aa = p.aa && S.bvh_kind == BVH_LIST;
+    S.p1.push_back(aa ? p.aa1 : p.rec1);
+    S.p2.push_back(aa ? p.aa2 : p.rec2);
     S.p3.push_back(p.rec3);
-    const unsigned dev_type = p.aa ? (unsigned)OBJ_AAQUAD : (unsigned)p.type;
+    const unsigned dev_type = aa ? (unsigned)OBJ_AAQUAD : (unsigned)p.type;
     S.slot_info.push_back(I2{p.mat, (int)((unsigned)p.obj | (dev_type << 30))});
     ExactPrim e;
     std::memset(&e, 0, sizeof(e));
