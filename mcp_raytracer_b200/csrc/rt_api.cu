@@ -21,6 +21,7 @@ bool render_needs_full(const DevScene& S, const RenderParams& R);
 cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* obj_id, float* t, float* normal,
                                  uint8_t* front, cudaStream_t st);
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
+cudaError_t launch_render_wavefront(const DevScene& S, const RenderParams& R, WfHost& H, int sms, cudaStream_t st, int* launches);
 cudaError_t launch_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches, cudaStream_t st);
 } // namespace rt
 
@@ -76,6 +77,8 @@ struct rt_camera {
   size_t scratch_elems = 0;
   int sms = 0;
   int chunks = 1;
+  WfHost wf{};          // wavefront integrator: path pool + queues (allocated on first use)
+  bool wf_ready = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
@@ -97,6 +100,14 @@ static void free_camera(rt_camera* c) {
   for (void* p : c->allocs) cudaFree(p);
   cudaFree(c->d_rgb8); cudaFree(c->d_linear); cudaFree(c->d_moments); cudaFree(c->d_ids);
   cudaFree(c->d_t); cudaFree(c->d_normal); cudaFree(c->d_front); cudaFree(c->d_stats); cudaFree(c->d_queue); cudaFree(c->d_scratch);
+  if (c->wf_ready) {
+    WfBuffers& W = c->wf.W;
+    cudaFree(W.ray_o); cudaFree(W.ray_d); cudaFree(W.tp); cudaFree(W.rad); cudaFree(W.pix);
+    for (int k = 0; k < WF_TAGS; ++k) cudaFree(W.q_shade[k]);
+    cudaFree(c->wf.q_extend[0]); cudaFree(c->wf.q_extend[1]); cudaFree(c->wf.q_free[0]); cudaFree(c->wf.q_free[1]);
+    cudaFree(W.counters); cudaFree(c->wf.owned_blocks);
+    cudaFreeHost(c->wf.h_counters);
+  }
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -155,8 +166,8 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
     delete c;
     return fail(RT_ERR_INVALID_ARGUMENT, "part_index out of range");
   }
-  if (opts->integrator == RT_INTEGRATOR_WAVEFRONT) { delete c; return fail(RT_ERR_UNSUPPORTED, "wavefront integrator not built in this round"); }
   c->opts = *opts;
+  c->integrator = opts->integrator == RT_INTEGRATOR_WAVEFRONT ? RT_INTEGRATOR_WAVEFRONT : RT_INTEGRATOR_MEGAKERNEL;
   int ndev = rt_device_count();
   if (ndev <= 0) { delete c; return fail(RT_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback"); }
   int dev = opts->device;
@@ -238,6 +249,54 @@ rt_status rt_camera_set_stream(rt_camera* c, void* s) {
   return RT_OK;
 }
 
+// Wavefront integrator: allocate the path pool once, list the 8x4 blocks this GPU owns in the region.
+static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
+  WfHost& H = c->wf;
+  const int blocks_x = P.tiles_x * 2, blocks_y = P.tiles_y * 4;
+  std::vector<int> owned;
+  owned.reserve((size_t)blocks_x * blocks_y);
+  for (int by = 0; by < blocks_y; ++by)
+    for (int bx = 0; bx < blocks_x; ++bx) {
+      const int tx = (P.x0 / 16) + (bx >> 1), ty = (P.y0 / 16) + (by >> 2);
+      if (P.part_count > 1 && ((tx + ty) % P.part_count) != P.part_index) continue;
+      const int px0 = (P.x0 / 16) * 16 + bx * 8, py0 = (P.y0 / 16) * 16 + by * 4;
+      if (px0 >= P.x1 || py0 >= P.y1 || px0 + 8 <= P.x0 || py0 + 4 <= P.y0) continue;
+      owned.push_back(by * blocks_x + bx);
+    }
+  if (!c->wf_ready) {
+    std::memset(&H, 0, sizeof(H));
+    static const int slots_env = getenv("RT_B200_WF_SLOTS") ? atoi(getenv("RT_B200_WF_SLOTS")) : 0;
+    const int n = slots_env > 0 ? slots_env : (1 << 22); // 4 Mi paths in flight, 80 B each
+    WfBuffers& W = H.W;
+    W.n_slots = n;
+    CU(cudaMalloc(&W.ray_o, (size_t)n * sizeof(F4)));
+    CU(cudaMalloc(&W.ray_d, (size_t)n * sizeof(F4)));
+    CU(cudaMalloc(&W.tp, (size_t)n * sizeof(F4)));
+    CU(cudaMalloc(&W.rad, (size_t)n * sizeof(F4)));
+    CU(cudaMalloc(&W.pix, (size_t)n * sizeof(U2)));
+    for (int k = 0; k < WF_TAGS; ++k) CU(cudaMalloc(&W.q_shade[k], (size_t)n * sizeof(int)));
+    for (int k = 0; k < 2; ++k) {
+      CU(cudaMalloc(&H.q_extend[k], (size_t)n * sizeof(int)));
+      CU(cudaMalloc(&H.q_free[k], (size_t)n * sizeof(int)));
+    }
+    CU(cudaMalloc(&W.counters, WFC_COUNT * sizeof(int)));
+    CU(cudaMallocHost(&H.h_counters, WFC_COUNT * sizeof(int)));
+    c->wf_ready = true;
+  }
+  if ((int)owned.size() > H.owned_capacity) {
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(H.owned_blocks);
+    H.owned_blocks = nullptr;
+    CU(cudaMalloc(&H.owned_blocks, std::max<size_t>(owned.size(), 1) * sizeof(int)));
+    H.owned_capacity = (int)owned.size();
+  }
+  if (!owned.empty()) CU(cudaMemcpy(H.owned_blocks, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice));
+  H.n_owned = (int)owned.size();
+  H.blocks_x = blocks_x;
+  H.W.total_pairs = (unsigned long long)owned.size() * 32ull * (unsigned long long)std::max(0, c->hs.cam.samples);
+  return RT_OK;
+}
+
 // enqueue: stats init, render kernel, optional stats finalisation.  No synchronisation.
 static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_dev, int* launches) {
   CU(cudaMemcpyAsync(c->d_stats, kStatsInit, sizeof(kStatsInit), cudaMemcpyHostToDevice, c->stream));
@@ -268,7 +327,8 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       c->queue_ints = need_q;
     }
     // fixed-point radiance sums [H][W][4] u64, only when a pixel's samples are split over CTAs
-    const size_t need_s = P.chunks > 1 ? (size_t)4 * c->hs.image_width * c->hs.image_height : 0;
+    const bool wavefront = c->integrator == RT_INTEGRATOR_WAVEFRONT && !render_needs_full(c->ds, P);
+    const size_t need_s = (P.chunks > 1 || wavefront) ? (size_t)4 * c->hs.image_width * c->hs.image_height : 0;
     if (need_s > c->scratch_elems) {
       CU(cudaStreamSynchronize(c->stream));
       cudaFree(c->d_scratch);
@@ -289,8 +349,14 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     P.queue = c->d_queue;
     P.tile_done = c->d_queue + 1;
     P.accum = c->d_scratch;
-    CU(launch_render_mega(c->ds, P, c->sms, c->stream));
-    *launches = 1;
+    if (wavefront) {
+      rt_status ws = wf_prepare(c, P);
+      if (ws != RT_OK) return ws;
+      CU(launch_render_wavefront(c->ds, P, c->wf, c->sms, c->stream, launches));
+    } else {
+      CU(launch_render_mega(c->ds, P, c->sms, c->stream));
+      *launches = 1;
+    }
   }
   if (stats_dev) {
     CU(launch_finalize_stats(c->d_stats, stats_dev, *launches + 1, c->stream));

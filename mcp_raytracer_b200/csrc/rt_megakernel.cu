@@ -226,7 +226,7 @@ RT_DEV void flush_stats(const RenderParams& R, unsigned n_pixels, int pixel_samp
   unsigned long long rs = warp_sum((unsigned long long)rays);
   int smin = warp_min(n_pixels ? pixel_samples : 0x7fffffff), smax = warp_max(n_pixels ? pixel_samples : 0);
   int bmin = warp_min(n_samples ? min_b : 0x7fffffff), bmax = warp_max(n_samples ? max_b : 0);
-  if ((threadIdx.x & 31) == 0 && (ss || px)) {
+  if ((threadIdx.x & 31) == 0 && (ss || px || rs)) {
     atomicAdd(R.stats + kStatPixels, px);
     atomicAdd(R.stats + kStatSamples, ss);
     atomicAdd(R.stats + kStatBounces, bs);
@@ -762,3 +762,5 @@ cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st)
 }
 
 } // namespace rt
+
+#include "rt_wavefront.cuh" // the wavefront integrator shares every helper above

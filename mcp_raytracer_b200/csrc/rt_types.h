@@ -123,6 +123,41 @@ struct RenderParams {
   int* tile_done;              // [8x4 blocks] finished chunks per block
   int trav_min_lanes;          // k_render_trav: leave the traversal phase when <= this many lanes still traverse
 };
+// ---- wavefront integrator (rt_wavefront.cuh): path pool + queues in HBM ----
+struct U2 { uint32_t x, y; };
+enum : int { WF_TAGS = 3 };
+enum : int { // indices into WfBuffers::counters (device ints)
+  WFC_NEXT_PAIR = 0,   // next (pixel, sample) pair index (64-bit: two ints)
+  WFC_NEXT_PAIR_HI,
+  WFC_N_EXTEND,        // rays queued for the next extend
+  WFC_EXTEND_CURSOR,   // extend's dynamic-fetch cursor
+  WFC_N_SHADE0, WFC_N_SHADE1, WFC_N_SHADE2,
+  WFC_N_FREE,          // free slots queued for the next generate
+  WFC_COUNT
+};
+struct WfBuffers {
+  F4* ray_o;   // o.xyz, hit t
+  F4* ray_d;   // d.xyz, hit slot (int bits)
+  F4* tp;      // throughput.xyz, bounces (int bits)
+  F4* rad;     // radiance.xyz, draws already taken from the current bounce's stream (int bits)
+  U2* pix;     // pixel index, sample index
+  int* q_extend;
+  int* q_shade[WF_TAGS];
+  int* q_free;
+  int* counters;
+  int n_slots;
+  unsigned long long total_pairs; // owned 8x4 blocks * 32 * samples
+};
+struct WfHost { // device allocations owned by the camera (rt_api.cu)
+  WfBuffers W;
+  int* q_extend[2];
+  int* q_free[2];
+  int* owned_blocks;
+  int* h_counters; // pinned host
+  int n_owned, blocks_x;
+  int owned_capacity;
+};
+
 enum : int {
   kStatPixels = 0, kStatSamples, kStatBounces, kStatRays,
   kStatSamplesMin, kStatSamplesMax, kStatBouncesMin, kStatBouncesMax, kStatCount
