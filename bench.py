@@ -73,21 +73,41 @@ def algorithmic_flops(cnt, n_lights, aperture):
 
 
 def cpu_reference_run(sd, opts, target_seconds, threads):
-    """Times the oracle on a bounded sample: the full image at a reduced spp chosen from a 1-spp
-    calibration so the run lasts about `target_seconds` (adaptive sampling is off, so cost is
-    linear in spp)."""
+    """Times the oracle on a BOUNDED sample of the workload that lasts about `target_seconds`: the same
+    scene and camera, first at a reduced spp (adaptive sampling is off, so cost is linear in spp) and,
+    if even 4 spp of the full image would take too long, at a reduced resolution as well (same field of
+    view, so the mix of paths is the same).  The size is chosen from a small calibration render, which
+    keeps the whole call bounded even where the reference's own BVH is nearly useless (its per-axis box
+    test, aabb.ts:30-59, accepts most boxes along a long ray: 100k-sphere rain scene)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_binding import OracleCamera
 
     base = dict(opts)
-    cal = dict(base, samples=2)
-    cam = OracleCamera(sd, cal)
-    t0 = time.perf_counter()
-    r = cam.render(threads=threads, want_counters=False)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    per_spp = dt / 2
-    spp = int(max(2, min(base["samples"], target_seconds / per_spp)))
-    cam = OracleCamera(sd, dict(base, samples=spp))
+    full_w, full_spp = int(base["width"]), int(base["samples"])
+    # calibration: grow a tiny render until it takes >= 0.2 s (or a hard cap of work is reached)
+    cal_w, cal_spp, per_path, ratio = min(full_w, 32), 1, None, 1.0
+    for _ in range(8):
+        cam = OracleCamera(sd, dict(base, width=cal_w, samples=cal_spp))
+        t0 = time.perf_counter()
+        r = cam.render(threads=threads)
+        dt = max(time.perf_counter() - t0, 1e-5)
+        ratio = cam.imageHeight / cam.imageWidth
+        per_path = dt / max(1, r["stats"].samples_total)
+        if dt >= 0.2 or (cal_w >= full_w and cal_spp >= full_spp):
+            break
+        if cal_w < min(full_w, 256):
+            cal_w = min(full_w, cal_w * 2)
+        else:
+            cal_spp = min(full_spp, cal_spp * 4)
+    budget_paths = target_seconds / per_path
+    full_pixels = full_w * max(1, round(full_w * ratio))
+    min_spp = min(full_spp, 4)
+    if budget_paths >= full_pixels * min_spp:
+        width, spp = full_w, int(max(min_spp, min(full_spp, budget_paths / full_pixels)))
+    else:
+        spp = min_spp
+        width = int(max(16, min(full_w, (budget_paths / (spp * ratio)) ** 0.5)))
+    cam = OracleCamera(sd, dict(base, width=width, samples=spp))
     t0 = time.perf_counter()
     r = cam.render(threads=threads, want_counters=True)
     dt = time.perf_counter() - t0
@@ -96,6 +116,7 @@ def cpu_reference_run(sd, opts, target_seconds, threads):
         "seconds": dt, "spp": spp, "paths": int(st.samples_total), "rays": int(st.rays), "counters": r["counters"],
         "n_lights": cam.n_lights, "width": cam.imageWidth, "height": cam.imageHeight,
         "mpaths_per_s": st.samples_total / dt / 1e6, "grays_per_s": st.rays / dt / 1e9,
+        "sample": f"{cam.imageWidth}x{cam.imageHeight} @{spp}spp, same scene and camera (full config: {full_w} wide @{full_spp}spp; adaptive off)",
     }
 
 
@@ -192,7 +213,7 @@ def main():
             if i >= args.warmup:
                 vals.append(last)
         v = sum(x["paths"] for x in vals) / sum(x["seconds"] for x in vals) / 1e6
-        sample = f"{last['width']}x{last['height']} full image @{last['spp']}spp of {ropts['samples']} (adaptive off: cost linear in spp)"
+        sample = last["sample"]
         line = {
             "impl": "reference", "metric": "Mpaths/s", "value": v, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * sum(x["seconds"] for x in vals) / len(vals), "higher_is_better": True,
@@ -337,7 +358,7 @@ def main():
         pass
     if not args.no_cpu_baseline:
         c = cpu_reference_run(sd, ropts, target_seconds=args.cpu_seconds, threads=cpu_threads)
-        sample = f"{c['width']}x{c['height']} full image @{c['spp']}spp of {ropts['samples']} (adaptive off: cost linear in spp)"
+        sample = c["sample"]
         cpu = {"value": c["mpaths_per_s"], "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
                "grays_per_s": c["grays_per_s"], "seconds": c["seconds"],
                "note": "C++ restatement of the TypeScript reference (cannot run here); row strips, one per thread, like src/raytracer.ts:60-90"}
