@@ -164,7 +164,7 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
     return false;
   }
   // camera.ts:285-315 with the mixture pdf of pdf.ts:57-99
-  const Onb onb = make_onb(sf.n);
+  const Onb onb = make_onb<true>(sf.n);
   const float rnd = g.next() * mw.total_w;
   const float r1 = g.next(), r2 = g.next();
   V3 dir = onb_local(onb, cosine_direction(r1, r2));
