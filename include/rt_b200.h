@@ -76,8 +76,11 @@ enum { RT_BVH_AUTO = 0, RT_BVH_REFERENCE = 1, RT_BVH_SAH = 2, RT_BVH_LIST = 3 };
 
 /* Device integrator layout.  MEGAKERNEL = register-resident paths with per-lane path
  * regeneration; WAVEFRONT = ray-gen / traverse / per-material shade kernels over path
- * queues in HBM.  Same estimator, same RNG streams, same image. */
-enum { RT_INTEGRATOR_AUTO = 0, RT_INTEGRATOR_MEGAKERNEL = 1, RT_INTEGRATOR_WAVEFRONT = 2 };
+ * queues in HBM; SORTED = the megakernel with a CTA-wide sort of the hits by material class
+ * between tracing and shading (shared memory; kernels without a sorted variant run as
+ * MEGAKERNEL).  Same estimator, same RNG streams, bit-identical image.  AUTO = SORTED when the
+ * scene has Mixed/Layered materials, else MEGAKERNEL. */
+enum { RT_INTEGRATOR_AUTO = 0, RT_INTEGRATOR_MEGAKERNEL = 1, RT_INTEGRATOR_WAVEFRONT = 2, RT_INTEGRATOR_SORTED = 3 };
 
 /* CameraData — src/scenes/sceneData.ts:22-37; defaults src/camera.ts:62-71 */
 typedef struct rt_camera_desc {

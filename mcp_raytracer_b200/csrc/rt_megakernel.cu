@@ -428,6 +428,387 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? 3 : RT_MIN_BLOCKS) k_r
 }
 
 // =========================================================================================
+// k_render_sorted — fixed spp, default mode: CTA-wide path pool, hits sorted by material class
+// between the trace and the shade phase.
+//
+// In k_render_pool about half of the issued instructions are shading code run by 10-50 % of a warp's
+// lanes (every lane's hit has its own material: walls, light, glass, miss).  Here the 256 threads of a
+// CTA share one pool of (pixel, sample) pairs (the eight warp items the warps popped), and every
+// iteration is
+//   A  trace      all threads, one ray each (converged: LIST tests every primitive for every ray)
+//   B  sort       class = material type of the hit | miss | idle; counting sort over the CTA:
+//                 match.any + popc inside a warp, 64 (class, warp) counts in shared memory, one
+//                 redundant 64-entry scan per warp (no third barrier)
+//   C  exchange   a thread writes its path (six 16-byte records) at the sorted position and takes the
+//                 path at position threadIdx.x: warps now hold one class each
+//   D  shade      path_post for the hit, exact fixed-point accumulation of finished paths, a new pair
+//                 from the pool for their threads (warp-aggregated shared atomic), then the Philox
+//                 block + roulette test of the next bounce for everybody
+// Two barriers per iteration.  A path killed by the roulette test keeps its thread for one idle trace
+// phase (slot = -2) so accumulation has a single call site.  Which thread runs which pair is
+// scheduling-dependent; the image is not (counter-based RNG + exact sums), so the output is
+// bit-identical to k_render_pool's.
+// =========================================================================================
+enum : int { CLS_MISS = 6, CLS_IDLE = 7, CLS_COUNT = 8 };
+
+struct SortSmem {
+  float4 st[6][256];            // G0 (o, t) G1 (d, slot) G2 (tp, bounces) G3 (radiance, item<<5|pixel) G4 (q0..q3) G5 (q4, avail|block<<3, pixel, sample)
+  unsigned int acc[8][32 * 9];  // per warp item: 32 pixels x 9 limbs (acc_add)
+  int cnt[CLS_COUNT * 8];       // [class][warp]
+  int it_px0[8], it_py0[8], it_sb[8], it_se[8], it_blk[8];
+  int cursor;
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 3) k_render_sorted(const DevScene S, const RenderParams R) {
+  __shared__ ListSmem sm;
+  __shared__ SortSmem ss;
+  const SmemList L = stage_list<KIND>(S, sm);
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned full = 0xffffffffu;
+
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  int st_bmin = 0x7fffffff, st_bmax = 0;
+
+  for (;;) {
+    // ---- CTA item = the eight warp items popped by the eight warps ----
+    {
+      WarpItem it{0, 0, 0, 0, 0};
+      const bool got = next_warp_item(R, cam.samples, lane, it);
+      if (lane == 0) {
+        ss.it_px0[warp] = it.px0; ss.it_py0[warp] = it.py0; ss.it_blk[warp] = it.blk;
+        ss.it_sb[warp] = got ? it.s_begin : 0; ss.it_se[warp] = got ? it.s_end : 0;
+      }
+      acc_clear(ss.acc[warp], lane);
+      if (tid == 0) ss.cursor = 0;
+    }
+    __syncthreads();
+    int maxlen = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) maxlen = max(maxlen, ss.it_se[k] - ss.it_sb[k]);
+    if (maxlen == 0) break; // the queue is exhausted for every warp
+    const int pool = maxlen * 256; // pair idx -> item idx & 7, pixel (idx >> 3) & 31, sample (idx >> 8); short items drop theirs
+
+    PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+    Rng g;
+    g.seed_lo = S.seed_lo; g.seed_hi = S.seed_hi;
+    g.k0 = g.k1 = g.stream = g.block = 0; g.q0 = g.q1 = g.q2 = g.q3 = g.q4 = 0; g.avail = 0;
+    uint32_t pixel = 0, sample = 0;
+    int wl = 0;
+    bool have = false, dead = false;
+
+    for (;;) {
+      // ---- A: trace ----
+      float t = CUDART_INF_F;
+      int slot = -1, key = CLS_IDLE;
+      if (have) {
+        int type = CLS_MISS;
+        if (dead) slot = -2;
+        else {
+          ++st_rays;
+          closest_hit<KIND>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
+          if (slot >= 0) {
+            const int root = KIND == BVH_LIST ? sm.mat[slot] : ldgi2(S.slot_info + slot).x;
+            type = __ldg(&S.matB[root].x);
+          }
+        }
+        // sort order: lambert, light, miss, metal, glass, mixed, layered — the class that shades longest
+        // comes first (its range starts warp-aligned) and shares its one mixed warp with the cheapest classes
+        key = (int)((0x2651430u >> (4 * type)) & 7u);
+      }
+      // ---- B: counting sort by class over the CTA ----
+      const unsigned grp = __match_any_sync(full, key);
+      if (lane < CLS_COUNT) ss.cnt[lane * 8 + warp] = 0;
+      __syncwarp();
+      if ((grp & lt_mask) == 0) ss.cnt[key * 8 + warp] = __popc(grp);
+      __syncthreads();
+      const int c0 = ss.cnt[2 * lane], c1 = ss.cnt[2 * lane + 1];
+      int incl = c0 + c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(full, incl, o);
+        if (lane >= (unsigned)o) incl += v;
+      }
+      const int excl = incl - (c0 + c1);
+      const int e = key * 8 + (int)warp;
+      int dst = __shfl_sync(full, excl, e >> 1);
+      const int c0e = __shfl_sync(full, c0, e >> 1);
+      if (e & 1) dst += c0e;
+      dst += __popc(grp & lt_mask);
+      const int n_live = __shfl_sync(full, excl, (CLS_IDLE * 8) >> 1); // paths in flight = first idle position
+      const bool exhausted = ss.cursor >= pool;
+      if (n_live == 0 && exhausted) break;
+      // ---- C: exchange ----
+      if (have) {
+        ss.st[0][dst] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, t);
+        ss.st[1][dst] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, __int_as_float(slot));
+        ss.st[2][dst] = make_float4(ps.tp.x, ps.tp.y, ps.tp.z, __int_as_float(ps.bounces));
+        ss.st[3][dst] = make_float4(ps.radiance.x, ps.radiance.y, ps.radiance.z, __int_as_float(wl));
+        ss.st[4][dst] = make_float4(__uint_as_float(g.q0), __uint_as_float(g.q1), __uint_as_float(g.q2), __uint_as_float(g.q3));
+        ss.st[5][dst] = make_float4(__uint_as_float(g.q4), __int_as_float(g.avail | (int)(g.block << 3)), __uint_as_float(pixel),
+                                    __uint_as_float(sample));
+      }
+      __syncthreads();
+      have = (int)tid < n_live;
+      if (have) {
+        const float4 a0 = ss.st[0][tid], a1 = ss.st[1][tid], a2 = ss.st[2][tid], a3 = ss.st[3][tid], a4 = ss.st[4][tid],
+                     a5 = ss.st[5][tid];
+        ps.ray.o = mk3(a0.x, a0.y, a0.z); t = a0.w;
+        ps.ray.d = mk3(a1.x, a1.y, a1.z); slot = __float_as_int(a1.w);
+        ps.tp = mk3(a2.x, a2.y, a2.z); ps.bounces = __float_as_int(a2.w);
+        ps.radiance = mk3(a3.x, a3.y, a3.z); wl = __float_as_int(a3.w);
+        g.q0 = __float_as_uint(a4.x); g.q1 = __float_as_uint(a4.y); g.q2 = __float_as_uint(a4.z); g.q3 = __float_as_uint(a4.w);
+        g.q4 = __float_as_uint(a5.x);
+        const int ab = __float_as_int(a5.y);
+        g.avail = ab & 7; g.block = (uint32_t)ab >> 3;
+        pixel = __float_as_uint(a5.z); sample = __float_as_uint(a5.w);
+        g.k0 = pixel; g.k1 = sample; g.stream = (uint32_t)ps.bounces;
+      }
+      // ---- D: shade, retire, refill, start the next bounce ----
+      bool start = false, fresh = false;
+      if (have) {
+        const bool fin = slot == -2 || path_post<KIND>(S, &sm, mw, ps, g, t, slot);
+        if (fin) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
+          acc_add(ss.acc[wl >> 5], wl & 31, ps.radiance);
+          ++st_paths;
+          st_bounces += (unsigned)ps.bounces;
+          st_bmin = min(st_bmin, ps.bounces);
+          st_bmax = max(st_bmax, ps.bounces);
+          have = false;
+        } else start = true;
+      }
+      int px = 0, py = 0;
+      const unsigned need = __ballot_sync(full, !have);
+      if (need != 0u && !exhausted) {
+        const int leader = __ffs(need) - 1;
+        int base = 0;
+        if ((int)lane == leader) base = atomicAdd(&ss.cursor, __popc(need));
+        base = __shfl_sync(full, base, leader);
+        const int idx = base + __popc(need & lt_mask);
+        if (!have && idx < pool) {
+          const int w = idx & 7, lp = (idx >> 3) & 31;
+          const int smp = ss.it_sb[w] + (idx >> 8);
+          px = ss.it_px0[w] + (lp & 7);
+          py = ss.it_py0[w] + (lp >> 3);
+          if (smp < ss.it_se[w] && px >= R.x0 && px < R.x1 && py >= R.y0 && py < R.y1) {
+            have = fresh = start = true;
+            wl = w * 32 + lp;
+            sample = (uint32_t)smp;
+            pixel = (uint32_t)py * (uint32_t)cam.width + (uint32_t)px;
+            ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0;
+          }
+        }
+      }
+      dead = false;
+      if (start) {
+        g.begin(pixel, sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
+        if (fresh) ps.ray = camera_ray(cam, px, py, g, true);
+        dead = path_pre(cam, ps, g);
+      }
+    }
+    __syncthreads(); // everybody has left the loop; accumulators are final
+    {
+      unsigned long long sum[3];
+      acc_read(ss.acc[warp], lane, sum);
+      const WarpItem it{ss.it_blk[warp], ss.it_px0[warp], ss.it_py0[warp], ss.it_sb[warp], ss.it_se[warp]};
+      if (it.s_end > it.s_begin) st_pixels += item_epilogue(R, cam, it, lane, sum);
+    }
+    __syncthreads(); // descriptors and accumulators are rewritten at the top
+  }
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+}
+
+// =========================================================================================
+// k_render_wq — fixed spp, default mode: warp-local wavefront.  A warp keeps NS > 32 paths of its item
+// in shared memory and runs STAGES over up to 32 of them at a time: "trace" (closest hit for paths
+// whose next ray is ready) and "shade" for the paths whose hit has one material class.  Every stage
+// takes the fullest queue, so a stage runs with (nearly) all lanes on one piece of code; nothing is
+// shared between warps, so there is no CTA barrier — only __syncwarp between stages.
+//   queues (stacks of slot numbers, counts in warp-uniform registers):
+//     0 lambert  1 metal  2 glass  3 done (light hit, miss, roulette kill, empty slot)  4 mixed  5 layered  6 trace
+//   shade stage: path_post; finished paths are accumulated (exact fixed point) and their slots take
+//   the next (pixel, sample) pairs of the item; then Philox block + roulette test of the next bounce.
+// Path records (88 B): G0 (o, t) G1 (d, slot) G2 (throughput, bounces) G3 (radiance, pixel | sample << 5)
+// G4 (q0..q3) G5 (q4, avail | block << 3).  Bit-identical to k_render_pool (counter-based RNG, exact sums).
+//
+// MEASURED AND NOT USED (compiled only with -DRT_EXPERIMENTAL_WQ; RT_B200_WQ=1..3 selects NS/CTAs):
+// lanes per instruction rise from 22 to 29.6 of 32, but queue upkeep + record traffic add ~390
+// instructions per ray to k_render_pool's ~980, and at 80 registers the records leave too little L1
+// for the spills.  Cornell 1024^2 @1024 spp: 153.5 ms (NS 96, 2 CTAs/SM) vs 128 ms for k_render_pool.
+// =========================================================================================
+#ifdef RT_EXPERIMENTAL_WQ
+enum : int { Q_DONE = 3, Q_TRACE = 6, Q_COUNT = 7 };
+enum : int { SLOT_DEAD = -2, SLOT_EMPTY = -3 };
+
+template <int NS>
+struct alignas(16) WqWarp {
+  float4 st[5][NS];
+  float2 st5[NS];
+  unsigned char q[Q_COUNT][NS];
+  unsigned int acc[32 * 9];
+};
+
+extern __shared__ __align__(16) unsigned char wq_smem[];
+
+template <int KIND, int NS, int BLOCKS>
+__global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, const RenderParams R) {
+  ListSmem& sm = *reinterpret_cast<ListSmem*>(wq_smem);
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  WqWarp<NS>& W = reinterpret_cast<WqWarp<NS>*>(wq_smem + (KIND == BVH_LIST ? sizeof(ListSmem) : 0))[warp];
+  const SmemList L = stage_list<KIND>(S, sm);
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const unsigned full = 0xffffffffu;
+
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  int st_bmin = 0x7fffffff, st_bmax = 0;
+
+  WarpItem it;
+  while (next_warp_item(R, cam.samples, lane, it)) {
+    const int pool = 32 * (it.s_end - it.s_begin); // (pixel, sample) pairs of this item
+    acc_clear(W.acc, lane);
+    int next = 0; // warp-uniform cursor into the pairs
+    for (int s = (int)lane; s < NS; s += 32) { // every slot starts empty in the "done" queue: the first stages fill them
+      W.q[Q_DONE][s] = (unsigned char)s;
+      W.st[1][s].w = __int_as_float(SLOT_EMPTY);
+    }
+    int n[Q_COUNT];
+#pragma unroll
+    for (int c = 0; c < Q_COUNT; ++c) n[c] = c == Q_DONE ? NS : 0;
+    __syncwarp();
+
+    for (;;) {
+      // ---- the fullest queue is the next stage ----
+      int best = Q_TRACE, cnt = n[Q_TRACE];
+#pragma unroll
+      for (int c = 0; c < Q_TRACE; ++c)
+        if (n[c] > cnt) { cnt = n[c]; best = c; }
+      if (cnt == 0) break;
+      const int k = min(cnt, 32), base = cnt - k;
+#pragma unroll
+      for (int c = 0; c < Q_COUNT; ++c)
+        if (c == best) n[c] = base;
+      const bool active = (int)lane < k;
+      const int idx = active ? (int)W.q[best][base + (int)lane] : 0;
+      int cls = -1; // queue this slot goes to next
+      if (best == Q_TRACE) {
+        if (active) {
+          const float4 a0 = W.st[0][idx], a1 = W.st[1][idx];
+          const Ray r{mk3(a0.x, a0.y, a0.z), mk3(a1.x, a1.y, a1.z)};
+          float t;
+          int slot;
+          ++st_rays;
+          closest_hit<KIND>(S, L, r, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
+          W.st[0][idx].w = t;
+          W.st[1][idx].w = __int_as_float(slot);
+          cls = Q_DONE;
+          if (slot >= 0) {
+            const int root = KIND == BVH_LIST ? sm.mat[slot] : ldgi2(S.slot_info + slot).x;
+            const int type = __ldg(&S.matB[root].x);
+            cls = type == MAT_LIGHT ? Q_DONE : type;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < Q_TRACE; ++c) {
+          const unsigned m = __ballot_sync(full, cls == c);
+          if (cls == c) W.q[c][n[c] + __popc(m & lt_mask)] = (unsigned char)idx;
+          n[c] += __popc(m);
+        }
+      } else {
+        PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+        Rng g;
+        g.seed_lo = S.seed_lo; g.seed_hi = S.seed_hi;
+        g.k0 = g.k1 = g.stream = g.block = 0; g.q0 = g.q1 = g.q2 = g.q3 = g.q4 = 0; g.avail = 0;
+        int lp = 0, slot = SLOT_EMPTY;
+        uint32_t sample = 0;
+        bool want = false, start = false, fresh = false;
+        if (active) {
+          const float4 a0 = W.st[0][idx], a1 = W.st[1][idx];
+          slot = __float_as_int(a1.w);
+          want = true;
+          if (slot != SLOT_EMPTY) {
+            const float4 a2 = W.st[2][idx], a3 = W.st[3][idx], a4 = W.st[4][idx];
+            const float2 a5 = W.st5[idx];
+            ps.ray.o = mk3(a0.x, a0.y, a0.z);
+            ps.ray.d = mk3(a1.x, a1.y, a1.z);
+            ps.tp = mk3(a2.x, a2.y, a2.z); ps.bounces = __float_as_int(a2.w);
+            ps.radiance = mk3(a3.x, a3.y, a3.z);
+            const int ls = __float_as_int(a3.w);
+            lp = ls & 31; sample = (uint32_t)ls >> 5;
+            g.q0 = __float_as_uint(a4.x); g.q1 = __float_as_uint(a4.y); g.q2 = __float_as_uint(a4.z); g.q3 = __float_as_uint(a4.w);
+            g.q4 = __float_as_uint(a5.x);
+            const int ab = __float_as_int(a5.y);
+            g.avail = ab & 7; g.block = (uint32_t)ab >> 3;
+            g.k0 = (uint32_t)(it.py0 + (lp >> 3)) * (uint32_t)cam.width + (uint32_t)(it.px0 + (lp & 7));
+            g.k1 = sample; g.stream = (uint32_t)ps.bounces;
+            const bool fin = slot == SLOT_DEAD || path_post<KIND>(S, &sm, mw, ps, g, a0.w, slot);
+            if (fin) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
+              acc_add(W.acc, lp, ps.radiance);
+              ++st_paths;
+              st_bounces += (unsigned)ps.bounces;
+              st_bmin = min(st_bmin, ps.bounces);
+              st_bmax = max(st_bmax, ps.bounces);
+            } else { want = false; start = true; }
+          }
+        }
+        // ---- finished and empty slots take the next pairs of the item ----
+        const unsigned need = __ballot_sync(full, want);
+        int px = 0, py = 0;
+        if (want) {
+          const int pair = next + __popc(need & lt_mask);
+          if (pair < pool) {
+            lp = pair & 31;
+            px = it.px0 + (lp & 7);
+            py = it.py0 + (lp >> 3);
+            if (px >= R.x0 && px < R.x1 && py >= R.y0 && py < R.y1) {
+              fresh = start = true;
+              sample = (uint32_t)(it.s_begin + (pair >> 5));
+              ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0;
+            } else { // pairs of pixels outside the region are dropped; the slot asks again
+              cls = Q_DONE;
+              W.st[1][idx].w = __int_as_float(SLOT_EMPTY);
+            }
+          }
+        }
+        next = min(next + __popc(need), pool);
+        if (start) {
+          const uint32_t pixel = (uint32_t)(it.py0 + (lp >> 3)) * (uint32_t)cam.width + (uint32_t)(it.px0 + (lp & 7));
+          g.begin(pixel, sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
+          if (fresh) ps.ray = camera_ray(cam, px, py, g, true);
+          const bool dead = path_pre(cam, ps, g);
+          cls = dead ? Q_DONE : Q_TRACE;
+          W.st[0][idx] = make_float4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, 0.f);
+          W.st[1][idx] = make_float4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, __int_as_float(SLOT_DEAD));
+          W.st[2][idx] = make_float4(ps.tp.x, ps.tp.y, ps.tp.z, __int_as_float(ps.bounces));
+          W.st[3][idx] = make_float4(ps.radiance.x, ps.radiance.y, ps.radiance.z, __int_as_float(lp | (int)(sample << 5)));
+          W.st[4][idx] = make_float4(__uint_as_float(g.q0), __uint_as_float(g.q1), __uint_as_float(g.q2), __uint_as_float(g.q3));
+          W.st5[idx] = make_float2(__uint_as_float(g.q4), __int_as_float(g.avail | (int)(g.block << 3)));
+        }
+        {
+          const unsigned m = __ballot_sync(full, cls == Q_TRACE);
+          if (cls == Q_TRACE) W.q[Q_TRACE][n[Q_TRACE] + __popc(m & lt_mask)] = (unsigned char)idx;
+          n[Q_TRACE] += __popc(m);
+          const unsigned md = __ballot_sync(full, cls == Q_DONE);
+          if (cls == Q_DONE) W.q[Q_DONE][n[Q_DONE] + __popc(md & lt_mask)] = (unsigned char)idx;
+          n[Q_DONE] += __popc(md);
+        }
+      }
+      __syncwarp();
+    }
+    unsigned long long sum[3];
+    acc_read(W.acc, lane, sum);
+    st_pixels += item_epilogue(R, cam, it, lane, sum);
+    __syncwarp(); // acc is cleared at the top of the next item
+  }
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+}
+#endif // RT_EXPERIMENTAL_WQ
+
+// =========================================================================================
 // k_render_trav — fixed spp, default mode, SAH trees: traversal interleaved with shading.
 // Lane states: NONE (needs a pair) -> BEGIN (bounce not started) -> TRACE (mid-traversal) ->
 // LEAF (leaf children of the last node wait to be intersected) -> TRACE ... -> HIT (closest hit known,
@@ -717,6 +1098,31 @@ static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderPa
   return cudaGetLastError();
 }
 
+#ifdef RT_EXPERIMENTAL_WQ
+template <int KIND, int NS, int BLOCKS>
+static cudaError_t launch_wq(const DevScene& S, const RenderParams& R, long long ctas_of_work, int sms, cudaStream_t st) {
+  auto kernel = k_render_wq<KIND, NS, BLOCKS>;
+  const int smem = (int)((KIND == BVH_LIST ? sizeof(ListSmem) : 0) + 8 * sizeof(WqWarp<NS>));
+  static cudaError_t attr = [&]() {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    // just enough shared memory for BLOCKS resident CTAs (1 KB per CTA is reserved); the rest stays L1
+    int pct = (int)((BLOCKS * (smem + 1024) * 100LL + 228 * 1024 - 1) / (228 * 1024));
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
+  }();
+  if (attr != cudaSuccess) return attr;
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  long long resident = (long long)sms * per_sm;
+  int grid = (int)(ctas_of_work < resident ? ctas_of_work : resident);
+  if (grid < 1) grid = 1;
+  kernel<<<grid, 256, smem, st>>>(S, R);
+  return cudaGetLastError();
+}
+#endif
+
 cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st) {
   if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
   const long long tiles = (long long)R.tiles_x * R.tiles_y;
@@ -731,13 +1137,34 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   const long long work = tiles * R.chunks;
   static const bool pool_list = getenv("RT_B200_POOL_LIST") != nullptr;   // development switches
   static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
+  static const bool env_sorted = getenv("RT_B200_SORTED") != nullptr;
+  const bool sorted_list = env_sorted || R.sorted;
   switch (S.bvh_kind) {
     case BVH_LIST:
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
+#ifdef RT_EXPERIMENTAL_WQ
+      {
+        static const int wq = getenv("RT_B200_WQ") ? atoi(getenv("RT_B200_WQ")) : 0;
+        if (wq == 1) return launch_wq<BVH_LIST, 48, 3>(S, R, work, sms, st);
+        if (wq == 2) return launch_wq<BVH_LIST, 64, 3>(S, R, work, sms, st);
+        if (wq == 3) return launch_wq<BVH_LIST, 96, 2>(S, R, work, sms, st);
+      }
+#endif
+      if (sorted_list) {
+        static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_LIST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                              57); // 3 CTAs x 43.4 KB fit the 132 KB split; the rest stays L1
+        if (carve != cudaSuccess) return carve;
+        return launch_persistent(k_render_sorted<BVH_LIST>, S, R, work, sms, st);
+      }
       return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
     case BVH_SAH:
       // shallow trees: a whole traversal is a few node visits and interleaving only costs (measured on
       // the 480-sphere and 55-object scenes); deep trees: lanes diverge by 10x in visit count and win.
+      if (sorted_list && S.n_nodes < 4096) {
+        static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
+        if (carve != cudaSuccess) return carve;
+        return launch_persistent(k_render_sorted<BVH_SAH>, S, R, work, sms, st);
+      }
       if (no_trav || S.n_nodes < 4096) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
       return launch_persistent(k_render_trav, S, R, work, sms, st);
     default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);

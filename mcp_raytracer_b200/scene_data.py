@@ -21,12 +21,13 @@ RT_OBJ_SPHERE, RT_OBJ_PLANE, RT_OBJ_QUAD = 0, 1, 2
 RT_MAT_LAMBERT, RT_MAT_METAL, RT_MAT_GLASS, RT_MAT_LIGHT, RT_MAT_MIXED, RT_MAT_LAYERED = range(6)
 RT_MODE_DEFAULT, RT_MODE_BOUNCES, RT_MODE_SAMPLES = 0, 1, 2
 RT_BVH_AUTO, RT_BVH_REFERENCE, RT_BVH_SAH, RT_BVH_LIST = 0, 1, 2, 3
-RT_INTEGRATOR_AUTO, RT_INTEGRATOR_MEGAKERNEL, RT_INTEGRATOR_WAVEFRONT = 0, 1, 2
+RT_INTEGRATOR_AUTO, RT_INTEGRATOR_MEGAKERNEL, RT_INTEGRATOR_WAVEFRONT, RT_INTEGRATOR_SORTED = 0, 1, 2, 3
 
 _OBJ_TYPES = {"sphere": RT_OBJ_SPHERE, "plane": RT_OBJ_PLANE, "quad": RT_OBJ_QUAD}
 _MODES = {"default": RT_MODE_DEFAULT, "bounces": RT_MODE_BOUNCES, "samples": RT_MODE_SAMPLES}
 _BVH = {"auto": RT_BVH_AUTO, "reference": RT_BVH_REFERENCE, "sah": RT_BVH_SAH, "list": RT_BVH_LIST}
-_INTEGRATORS = {"auto": RT_INTEGRATOR_AUTO, "megakernel": RT_INTEGRATOR_MEGAKERNEL, "wavefront": RT_INTEGRATOR_WAVEFRONT}
+_INTEGRATORS = {"auto": RT_INTEGRATOR_AUTO, "megakernel": RT_INTEGRATOR_MEGAKERNEL, "wavefront": RT_INTEGRATOR_WAVEFRONT,
+                "sorted": RT_INTEGRATOR_SORTED}
 
 
 class RaytracerError(Exception):

@@ -352,6 +352,30 @@ def test_wavefront_integrator_equals_megakernel(gpu, name, width, spp):
     assert (sa.pixels, sa.samples, sa.bounces, sa.rays) == (sb.pixels, sb.samples, sb.bounces, sb.rays)
 
 
+@pytest.mark.parametrize("name,width,spp,bvh", [("C2-cornell", 200, 40, "auto"), ("C5-layered", 160, 24, "auto"), ("C1-spheres", 240, 16, "sah"),
+                                                ("default", 200, 16, "auto"), ("C4-rain", 160, 4, "auto")])
+def test_sorted_integrator_equals_megakernel(gpu, name, width, spp, bvh):
+    """CTA-wide sort of the hits by material class (k_render_sorted): other threads run the samples, same image.
+    C4 has no sorted kernel (deep tree) and must fall back to the plain megakernel."""
+    sd = SCENES[name]()
+    opts = {"width": width, "samples": spp, "aTolerance": 0, "seed": 5, "bvh": bvh}
+    a = gpu_render(sd, {**opts, "integrator": "megakernel"})
+    b = gpu_render(sd, {**opts, "integrator": "sorted"})
+    assert np.array_equal(a["rgb8"], b["rgb8"]) and np.array_equal(a["linear"], b["linear"])
+    sa, sb = a["stats"], b["stats"]
+    assert (sa.pixels, sa.samples, sa.bounces, sa.rays) == (sb.pixels, sb.samples, sb.bounces, sb.rays)
+    # region + 3-way partition through the sorted kernel
+    H, W = a["rgb8"].shape[:2]
+    buf = np.full((H, W, 3), 77, np.uint8)
+    reg = {"x": 11, "y": 5, "width": W // 2 + 1, "height": H // 2 + 3}
+    for k in range(3):
+        with createCameraFromSceneData(sd, {**opts, "integrator": "sorted", "partIndex": k, "partCount": 3}) as cam:
+            cam.renderRegion(buf, reg)
+    inside = np.zeros((H, W), bool)
+    inside[reg["y"]:reg["y"] + reg["height"], reg["x"]:reg["x"] + reg["width"]] = True
+    assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], a["rgb8"][inside])
+
+
 def test_wavefront_region_and_partition(gpu):
     sd = SCENES["C2-cornell"]()
     opts = {"width": 100, "samples": 8, "aTolerance": 0, "seed": 9}
