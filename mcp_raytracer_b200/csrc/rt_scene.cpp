@@ -16,11 +16,16 @@
 #include "rt_scene.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 namespace rt {
 namespace {
@@ -237,60 +242,82 @@ struct RefBuilder { // src/geometry/bvh.ts:34-102
   }
 };
 
+// Binned-SAH builder (16 bins, leaves <= 4) over compact records that are partitioned in place, so every
+// pass streams through memory.  The top of the tree is split serially into up to 16 subtrees that are
+// built by std::thread workers into private node pools and spliced in afterwards; split decisions do not
+// depend on the thread count, so the tree (and the image) is the same on every machine.
+struct SahRec {
+  float mn[3], mx[3], c[3];
+  int pi;
+};
+
 struct SahBuilder {
-  const std::vector<Prim>& P;
-  std::vector<BNode>& pool;
+  static constexpr int NB = 16;
   static double area(const Box& b) {
     double dx = (double)b.mx[0] - b.mn[0], dy = (double)b.mx[1] - b.mn[1], dz = (double)b.mx[2] - b.mn[2];
     if (dx < 0 || dy < 0 || dz < 0) return 0;
     return 2 * (dx * dy + dy * dz + dz * dx);
   }
-  int make_leaf(const std::vector<int>& idx, size_t b, size_t e) {
-    BNode n;
-    n.leaf = true;
-    n.box = empty_box();
-    for (size_t i = b; i < e; ++i) { n.prims.push_back(idx[i]); n.box = merge(n.box, P[idx[i]].sah_box); }
-    pool.push_back(n);
-    return (int)pool.size() - 1;
+  static Box box_of(const SahRec& r) {
+    Box b;
+    for (int a = 0; a < 3; ++a) { b.mn[a] = r.mn[a]; b.mx[a] = r.mx[a]; }
+    return b;
   }
-  int build(std::vector<int>& idx, size_t b, size_t e, int depth) {
-    size_t n = e - b;
-    if (n <= 2) return make_leaf(idx, b, e);
-    Box bounds = empty_box(), cb = empty_box();
-    auto centroid = [&](int pi, int ax) { return 0.5f * (P[pi].sah_box.mn[ax] + P[pi].sah_box.mx[ax]); };
-    for (size_t i = b; i < e; ++i) {
-      bounds = merge(bounds, P[idx[i]].sah_box);
+  static int make_leaf(const SahRec* r, size_t n, std::vector<BNode>& out) {
+    BNode nd;
+    nd.leaf = true;
+    nd.box = empty_box();
+    nd.prims.reserve(n);
+    for (size_t i = 0; i < n; ++i) { nd.prims.push_back(r[i].pi); nd.box = merge(nd.box, box_of(r[i])); }
+    out.push_back(std::move(nd));
+    return (int)out.size() - 1;
+  }
+  // One split decision.  Returns 0 for "make a leaf", else the size of the left part (records partitioned).
+  static size_t split(SahRec* r, size_t n, int depth, Box& bounds) {
+    bounds = empty_box();
+    Box cb = empty_box();
+    for (size_t i = 0; i < n; ++i) {
       for (int ax = 0; ax < 3; ++ax) {
-        float c = centroid(idx[i], ax);
-        cb.mn[ax] = std::min(cb.mn[ax], c);
-        cb.mx[ax] = std::max(cb.mx[ax], c);
+        bounds.mn[ax] = std::min(bounds.mn[ax], r[i].mn[ax]);
+        bounds.mx[ax] = std::max(bounds.mx[ax], r[i].mx[ax]);
+        cb.mn[ax] = std::min(cb.mn[ax], r[i].c[ax]);
+        cb.mx[ax] = std::max(cb.mx[ax], r[i].c[ax]);
       }
     }
-    const int NB = 16;
+    if (n <= 2) return 0;
+    Box bb[3][NB];
+    int cnt[3][NB];
+    float lo[3], scale[3];
+    bool use[3];
+    for (int ax = 0; ax < 3; ++ax) {
+      lo[ax] = cb.mn[ax];
+      use[ax] = cb.mx[ax] > cb.mn[ax];
+      scale[ax] = use[ax] ? NB / (cb.mx[ax] - cb.mn[ax]) : 0.f;
+      for (int k = 0; k < NB; ++k) { bb[ax][k] = empty_box(); cnt[ax][k] = 0; }
+    }
+    for (size_t i = 0; i < n; ++i) {
+      const Box b = box_of(r[i]);
+      for (int ax = 0; ax < 3; ++ax) {
+        if (!use[ax]) continue;
+        int k = std::min(NB - 1, std::max(0, (int)((r[i].c[ax] - lo[ax]) * scale[ax])));
+        cnt[ax][k]++;
+        bb[ax][k] = merge(bb[ax][k], b);
+      }
+    }
     double best_cost = std::numeric_limits<double>::infinity();
     int best_axis = -1, best_split = -1;
     for (int ax = 0; ax < 3; ++ax) {
-      float lo = cb.mn[ax], hi = cb.mx[ax];
-      if (!(hi > lo)) continue;
-      Box bb[NB];
-      int cnt[NB];
-      for (int k = 0; k < NB; ++k) { bb[k] = empty_box(); cnt[k] = 0; }
-      float scale = NB / (hi - lo);
-      for (size_t i = b; i < e; ++i) {
-        int k = std::min(NB - 1, std::max(0, (int)((centroid(idx[i], ax) - lo) * scale)));
-        cnt[k]++;
-        bb[k] = merge(bb[k], P[idx[i]].sah_box);
-      }
+      if (!use[ax]) continue;
       double ra[NB];
       int rc[NB];
       Box acc = empty_box();
       int c = 0;
-      for (int k = NB - 1; k >= 1; --k) { acc = merge(acc, bb[k]); c += cnt[k]; ra[k] = area(acc); rc[k] = c; }
+      for (int k = NB - 1; k >= 1; --k) { acc = merge(acc, bb[ax][k]); c += cnt[ax][k]; ra[k] = area(acc); rc[k] = c; }
       acc = empty_box();
       c = 0;
       for (int k = 0; k < NB - 1; ++k) {
-        acc = merge(acc, bb[k]);
-        c += cnt[k];
+        acc = merge(acc, bb[ax][k]);
+        c += cnt[ax][k];
         if (c == 0 || rc[k + 1] == 0) continue;
         double cost = area(acc) * c + ra[k + 1] * rc[k + 1];
         if (cost < best_cost) { best_cost = cost; best_axis = ax; best_split = k; }
@@ -298,38 +325,112 @@ struct SahBuilder {
     }
     size_t mid;
     if (best_axis < 0 || depth > 56) {
-      if (n <= 4) return make_leaf(idx, b, e);
+      if (n <= 4) return 0;
       // degenerate centroids (or a runaway depth): median split on the widest axis
       int ax = 0;
       float w = -1;
       for (int a = 0; a < 3; ++a) { float d = bounds.mx[a] - bounds.mn[a]; if (d > w) { w = d; ax = a; } }
-      mid = b + n / 2;
-      std::nth_element(idx.begin() + b, idx.begin() + mid, idx.begin() + e,
-                       [&](int x, int y) { return centroid(x, ax) < centroid(y, ax); });
+      mid = n / 2;
+      std::nth_element(r, r + mid, r + n, [ax](const SahRec& x, const SahRec& y) { return x.c[ax] < y.c[ax]; });
     } else {
       if (n <= 4) {
         // leaf cost (n prim tests) vs split cost (2 box tests + expected prim tests)
         double leaf_cost = (double)n;
         double split_cost = 1.2 + best_cost / std::max(area(bounds), 1e-30);
-        if (leaf_cost <= split_cost) return make_leaf(idx, b, e);
+        if (leaf_cost <= split_cost) return 0;
       }
-      float lo = cb.mn[best_axis], hi = cb.mx[best_axis];
-      float scale = NB / (hi - lo);
-      auto it = std::partition(idx.begin() + b, idx.begin() + e, [&](int pi) {
-        int k = std::min(NB - 1, std::max(0, (int)((centroid(pi, best_axis) - lo) * scale)));
-        return k <= best_split;
+      const float l = lo[best_axis], sc = scale[best_axis];
+      const int ax = best_axis, bs = best_split;
+      SahRec* it = std::partition(r, r + n, [=](const SahRec& x) {
+        int k = std::min(NB - 1, std::max(0, (int)((x.c[ax] - l) * sc)));
+        return k <= bs;
       });
-      mid = (size_t)(it - idx.begin());
-      if (mid == b || mid == e) mid = b + n / 2;
+      mid = (size_t)(it - r);
+      if (mid == 0 || mid == n) mid = n / 2;
     }
-    int l = build(idx, b, mid, depth + 1);
-    int r = build(idx, mid, e, depth + 1);
+    return mid;
+  }
+  static int build(SahRec* r, size_t n, int depth, std::vector<BNode>& out) {
+    Box bounds;
+    const size_t mid = split(r, n, depth, bounds);
+    if (mid == 0) return make_leaf(r, n, out);
+    const int l = build(r, mid, depth + 1, out);
+    const int rr = build(r + mid, n - mid, depth + 1, out);
     BNode node;
     node.left = l;
-    node.right = r;
-    node.box = merge(pool[l].box, pool[r].box);
-    pool.push_back(node);
-    return (int)pool.size() - 1;
+    node.right = rr;
+    node.box = bounds; // = merge of the children's boxes (every box is the bounds of its records)
+    out.push_back(std::move(node));
+    return (int)out.size() - 1;
+  }
+
+  struct Task {
+    SahRec* r;
+    size_t n;
+    int depth;
+    std::vector<BNode> local;
+    int root = -1;
+  };
+  // top of the tree: children that became tasks are recorded as -(task + 2)
+  static int build_top(SahRec* r, size_t n, int depth, int levels, std::vector<BNode>& out, std::vector<Task>& tasks) {
+    if (levels == 0 || n < 4096) {
+      tasks.push_back(Task{r, n, depth, {}, -1});
+      return -((int)tasks.size() - 1 + 2);
+    }
+    Box bounds;
+    const size_t mid = split(r, n, depth, bounds);
+    if (mid == 0) return make_leaf(r, n, out);
+    const int l = build_top(r, mid, depth + 1, levels - 1, out, tasks);
+    const int rr = build_top(r + mid, n - mid, depth + 1, levels - 1, out, tasks);
+    BNode node;
+    node.left = l;
+    node.right = rr;
+    node.box = bounds;
+    out.push_back(std::move(node));
+    return (int)out.size() - 1;
+  }
+  static int build_all(const std::vector<Prim>& P, const std::vector<int>& prims, std::vector<BNode>& pool) {
+    std::vector<SahRec> recs(prims.size());
+    for (size_t i = 0; i < prims.size(); ++i) {
+      const Box& b = P[prims[i]].sah_box;
+      SahRec& r = recs[i];
+      for (int a = 0; a < 3; ++a) { r.mn[a] = b.mn[a]; r.mx[a] = b.mx[a]; r.c[a] = 0.5f * (b.mn[a] + b.mx[a]); }
+      r.pi = prims[i];
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    if (recs.size() < 32768 || hw < 2) return build(recs.data(), recs.size(), 0, pool);
+    std::vector<Task> tasks;
+    tasks.reserve(16);
+    int root = build_top(recs.data(), recs.size(), 0, 4, pool, tasks);
+    {
+      std::atomic<size_t> next{0};
+      auto work = [&]() {
+        for (size_t k; (k = next.fetch_add(1)) < tasks.size();) {
+          Task& t = tasks[k];
+          t.local.reserve(t.n);
+          t.root = build(t.r, t.n, t.depth, t.local);
+        }
+      };
+      const unsigned nthreads = std::min<unsigned>(std::min<unsigned>(hw, 8u), (unsigned)tasks.size());
+      std::vector<std::thread> th;
+      for (unsigned k = 1; k < nthreads; ++k) th.emplace_back(work);
+      work();
+      for (auto& t : th) t.join();
+    }
+    // splice the private pools in and patch the placeholders
+    std::vector<int> task_root(tasks.size());
+    for (size_t k = 0; k < tasks.size(); ++k) {
+      const int off = (int)pool.size();
+      for (BNode& nd : tasks[k].local) {
+        if (!nd.leaf) { nd.left += off; nd.right += off; }
+        pool.push_back(std::move(nd));
+      }
+      task_root[k] = tasks[k].root + off;
+    }
+    auto fix = [&](int& ref) { if (ref <= -2) ref = task_root[(size_t)(-ref - 2)]; };
+    for (BNode& nd : pool) if (!nd.leaf) { fix(nd.left); fix(nd.right); }
+    fix(root);
+    return root;
   }
 };
 
@@ -339,15 +440,22 @@ struct Flattener {
   HostScene& S;
   const std::vector<int>& rank; // per object: position in the reference's visiting order
   int max_depth = 0;
-  bool has_inverted(int bi) const { // does the subtree hold a primitive whose reference box is inverted?
+  std::vector<signed char> inv_memo; // per build node: -1 unknown, 0/1
+  bool has_inverted(int bi) { // does the subtree hold a primitive whose reference box is inverted?
+    if (inv_memo.size() != pool.size()) inv_memo.assign(pool.size(), -1);
+    if (inv_memo[bi] >= 0) return inv_memo[bi] != 0;
     const BNode& n = pool[bi];
+    bool inv = false;
     if (n.leaf) {
       for (int pi : n.prims)
         for (int a = 0; a < 3; ++a)
-          if (P[pi].ref_box.mn[a] > P[pi].ref_box.mx[a]) return true;
-      return false;
+          if (P[pi].ref_box.mn[a] > P[pi].ref_box.mx[a]) inv = true;
+    } else {
+      const bool l = has_inverted(n.left), r = has_inverted(n.right); // both: every node of the subtree gets its memo
+      inv = l || r;
     }
-    return has_inverted(n.left) || has_inverted(n.right);
+    inv_memo[bi] = inv ? 1 : 0;
+    return inv;
   }
   void push_slot(int pi) {
     const Prim& p = P[pi];
@@ -411,6 +519,15 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     err = "invalid render options (width/aspect/samples/depth/aBatch)";
     return RT_ERR_INVALID_ARGUMENT;
   }
+  // RT_B200_BUILD_TRACE=1: stage times of the scene compiler on stderr (development aid)
+  static const bool trace = std::getenv("RT_B200_BUILD_TRACE") != nullptr;
+  auto t_last = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!trace) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[rt_b200 build] %-12s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   // ---- materials (createMaterial, scenes.ts:144-199) ----
   const uint32_t nm = sd->n_materials;
   S.matA.resize(nm); S.matB.resize(nm); S.matE.resize(nm);
@@ -449,6 +566,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     S.matB[i] = I4{ty, c0, c1, has_e ? 1 : 0};
     S.matE[i] = F4{emit[0], emit[1], emit[2], has_e ? 1.f : 0.f};
   }
+  lap("materials");
   // ---- objects (createSceneObject, scenes.ts:109-139) ----
   const uint32_t n = sd->n_objects;
   std::vector<Prim> P(n);
@@ -494,6 +612,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     L.slot = (int)i; // object index; resolved to a slot below
     S.lights.push_back(L);
   }
+  lap("objects");
   // ---- acceleration structure ----
   int kind = o->bvh;
   if (kind == RT_BVH_AUTO) {
@@ -528,6 +647,8 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     };
     walk(ref_root);
   }
+  S.p0.reserve(n); S.p1.reserve(n); S.p2.reserve(n); S.p3.reserve(n); S.slot_info.reserve(n); S.exact.reserve(n);
+  S.nodes.reserve(n);
   Flattener fl{P, kind == BVH_SAH ? pool : ref_pool, S, rank};
   if (kind == BVH_LIST) {
     // Slots in the reference's visiting order; only the box tests are dropped, which cannot
@@ -565,13 +686,14 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     (void)any_unbounded;
     if (!bounded.empty()) {
       pool.reserve(bounded.size());
-      SahBuilder sb{P, pool};
-      int root = sb.build(bounded, 0, bounded.size(), 0);
+      int root = SahBuilder::build_all(P, bounded, pool);
+      lap("sah build");
       S.nodes.emplace_back();
       if (pool[root].leaf) fl.fill_pair(0, root, -1, 0);
       else fl.fill_pair(0, pool[root].left, pool[root].right, 0);
     }
   }
+  lap("flatten");
   S.max_depth = fl.max_depth;
   if (S.max_depth > 60) { err = "BVH too deep"; return RT_ERR_UNSUPPORTED; }
   // resolve light slots

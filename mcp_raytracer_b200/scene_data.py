@@ -183,27 +183,40 @@ class FlatScene:
 
         objs = sceneData["objects"]
         n = len(objs)
-        self.obj_type = np.zeros(n, np.uint8)
-        self.obj_pos = np.zeros((n, 3), np.float64)
-        self.obj_u = np.zeros((n, 3), np.float64)
-        self.obj_v = np.zeros((n, 3), np.float64)
-        self.obj_r = np.zeros(n, np.float64)
-        self.obj_material = np.zeros(n, np.int32)
-        self.obj_light = np.zeros(n, np.uint8)
-        for i, ob in enumerate(objs):
+        # plain lists, converted once: a 100k-object scene spends its time here otherwise
+        types: List[int] = []
+        mats: List[int] = []
+        pos: List[Any] = []
+        us: List[Any] = []
+        vs: List[Any] = []
+        rs: List[float] = []
+        lights: List[int] = []
+        zero3 = (0.0, 0.0, 0.0)
+        for ob in objs:
             # scenes.ts:113 creates the material first, then switches on the object type
-            self.obj_material[i] = self._material(ob.get("material"), materials)
+            mats.append(self._material(ob.get("material"), materials))
             t = ob.get("type")
-            if t not in _OBJ_TYPES:
+            code = _OBJ_TYPES.get(t) if isinstance(t, str) else None
+            if code is None:
                 raise RaytracerError(f"Unknown object type: {t}")  # scenes.ts:137
-            self.obj_type[i] = _OBJ_TYPES[t]
-            self.obj_pos[i] = ob["pos"]
-            if t == "sphere":
-                self.obj_r[i] = ob["r"]
+            types.append(code)
+            pos.append(ob["pos"])
+            if code == RT_OBJ_SPHERE:
+                rs.append(ob["r"])
+                us.append(zero3)
+                vs.append(zero3)
             else:
-                self.obj_u[i] = ob["u"]
-                self.obj_v[i] = ob["v"]
-            self.obj_light[i] = 1 if ob.get("light") else 0
+                rs.append(0.0)
+                us.append(ob["u"])
+                vs.append(ob["v"])
+            lights.append(1 if ob.get("light") else 0)
+        self.obj_type = np.array(types, np.uint8).reshape(n)
+        self.obj_pos = np.ascontiguousarray(np.array(pos, np.float64).reshape(n, 3))
+        self.obj_u = np.ascontiguousarray(np.array(us, np.float64).reshape(n, 3))
+        self.obj_v = np.ascontiguousarray(np.array(vs, np.float64).reshape(n, 3))
+        self.obj_r = np.array(rs, np.float64).reshape(n)
+        self.obj_material = np.array(mats, np.int32).reshape(n)
+        self.obj_light = np.array(lights, np.uint8).reshape(n)
 
         self.mat_type_a = np.asarray(self.mat_type, np.uint8)
         self.mat_color_a = np.asarray(self.mat_color, np.float64).reshape(-1, 3)
@@ -234,10 +247,11 @@ class FlatScene:
 
     # -- createMaterial / createDielectric, src/scenes/scenes.ts:144-199 --
     def _node(self, ty: int, color=(0.0, 0.0, 0.0), param: float = 0.0, child=(-1, -1)) -> int:
+        # values are converted (and type-checked) once by numpy at the end of __init__
         self.mat_type.append(ty)
-        self.mat_color.append([float(color[0]), float(color[1]), float(color[2])])
-        self.mat_param.append(float(param))
-        self.mat_child.append([int(child[0]), int(child[1])])
+        self.mat_color.append(color if len(color) == 3 else (color[0], color[1], color[2]))
+        self.mat_param.append(param)
+        self.mat_child.append(child)
         return len(self.mat_type) - 1
 
     def _material(self, ref: Union[str, Dict[str, Any], None], materials: Dict[str, Any], depth: int = 0) -> int:
