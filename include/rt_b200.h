@@ -225,6 +225,10 @@ int32_t rt_abi_version(void);
 /* measured FP32 FMA throughput of `device` in TFLOP/s (dependent-chain FFMA microbenchmark),
  * the roofline denominator for this path. */
 rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz);
+/* Device buffers of destroyed cameras are kept for the next rt_camera_create (the reference builds
+ * its scene per request, src/render-utils/renderWorker.ts:20; cudaMalloc/cudaFree per image cost
+ * more than the scene build).  This returns them to the driver; result = bytes released. */
+uint64_t rt_trim_device_cache(void);
 
 #ifdef __cplusplus
 }

@@ -216,3 +216,8 @@ def measureFp32Peak(device: int = -1):
     if st != 0:
         raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
     return t.value, mhz.value
+
+
+def trimDeviceCache() -> int:
+    """Return the device buffers kept from destroyed cameras to the driver (rt_trim_device_cache); bytes released."""
+    return int(_native.lib().rt_trim_device_cache())

@@ -7,7 +7,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/rt_b200.h"
@@ -37,6 +40,89 @@ static rt_status fail(rt_status st, const std::string& msg) {
     cudaError_t e_ = (call);                                                                          \
     if (e_ != cudaSuccess) return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device memory cache.  The reference builds its scene objects per request and per worker
+// (renderWorker.ts:20), so a drop-in creates and destroys a camera per image; cudaMalloc/cudaFree
+// of the image-sized buffers then cost more than compiling the scene (cudaFree of the 32 MB
+// accumulator was measured at 100-170 ms every other call).  Freed blocks stay in a per-device
+// size-class list (8 classes per octave, <= 12.5 % slack) and are handed out again;
+// rt_trim_device_cache() gives them back to the driver.  Blocks are only reused after the stream of
+// the camera that owned them was synchronised (free_camera does that).
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks; // (device, class size) -> block
+  std::unordered_map<void*, std::pair<int, size_t>> live;   // block -> (device, class size)
+  size_t cached_bytes = 0;
+};
+DevCache& dev_cache() {
+  static DevCache* c = new DevCache(); // never destroyed: cameras may outlive static destructors
+  return *c;
+}
+const size_t kDevCacheMax = (size_t)4 << 30;
+size_t dev_class_size(size_t n) {
+  if (n <= 512) return 512;
+  int lg = 63 - __builtin_clzll((unsigned long long)(n - 1)); // 2^lg < n <= 2^(lg+1)
+  size_t step = (size_t)1 << (lg - 3);                        // 8 classes per octave (lg >= 9 here)
+  return (n + step - 1) / step * step;
+}
+size_t dev_trim_locked(DevCache& C) {
+  size_t freed = 0;
+  for (auto& kv : C.free_blocks) {
+    int prev = -1;
+    cudaGetDevice(&prev);
+    if (prev != kv.first.first) cudaSetDevice(kv.first.first);
+    cudaFree(kv.second);
+    if (prev >= 0 && prev != kv.first.first) cudaSetDevice(prev);
+    freed += kv.first.second;
+  }
+  C.free_blocks.clear();
+  C.cached_bytes = 0;
+  return freed;
+}
+template <class T>
+cudaError_t dev_alloc(T** out, size_t n) {
+  *out = nullptr;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const size_t cls = dev_class_size(n);
+  DevCache& C = dev_cache();
+  std::lock_guard<std::mutex> lk(C.mu);
+  auto it = C.free_blocks.find({dev, cls});
+  void* p = nullptr;
+  if (it != C.free_blocks.end()) {
+    p = it->second;
+    C.free_blocks.erase(it);
+    C.cached_bytes -= cls;
+  } else {
+    e = cudaMalloc(&p, cls);
+    if (e != cudaSuccess) { // give the cached blocks back and try once more
+      cudaGetLastError();
+      dev_trim_locked(C);
+      e = cudaMalloc(&p, cls);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  C.live[p] = {dev, cls};
+  *out = (T*)p;
+  return cudaSuccess;
+}
+void dev_free(void* p) {
+  if (!p) return;
+  DevCache& C = dev_cache();
+  std::lock_guard<std::mutex> lk(C.mu);
+  auto it = C.live.find(p);
+  if (it == C.live.end()) { cudaFree(p); return; }
+  const std::pair<int, size_t> key = it->second;
+  C.live.erase(it);
+  if (C.cached_bytes + key.second > kDevCacheMax) { cudaFree(p); return; }
+  C.free_blocks.insert({key, p});
+  C.cached_bytes += key.second;
+}
+} // namespace
 
 struct DeviceGuard { // switch to the camera's device for the duration of a call
   int prev = -1;
@@ -87,7 +173,7 @@ static rt_status upload(rt_camera* c, const std::vector<T>& v, const T** out) {
   *out = nullptr;
   if (v.empty()) return RT_OK;
   void* p = nullptr;
-  CU(cudaMalloc(&p, v.size() * sizeof(T)));
+  CU(dev_alloc(&p, v.size() * sizeof(T)));
   c->allocs.push_back(p);
   CU(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
   *out = (const T*)p;
@@ -97,15 +183,16 @@ static rt_status upload(rt_camera* c, const std::vector<T>& v, const T** out) {
 static void free_camera(rt_camera* c) {
   if (!c) return;
   DeviceGuard g(c->device);
-  for (void* p : c->allocs) cudaFree(p);
-  cudaFree(c->d_rgb8); cudaFree(c->d_linear); cudaFree(c->d_moments); cudaFree(c->d_ids);
-  cudaFree(c->d_t); cudaFree(c->d_normal); cudaFree(c->d_front); cudaFree(c->d_stats); cudaFree(c->d_queue); cudaFree(c->d_scratch);
+  cudaStreamSynchronize(c->stream); // the blocks go back to the cache: nothing of this camera may still be in flight
+  for (void* p : c->allocs) dev_free(p);
+  dev_free(c->d_rgb8); dev_free(c->d_linear); dev_free(c->d_moments); dev_free(c->d_ids);
+  dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch);
   if (c->wf_ready) {
     WfBuffers& W = c->wf.W;
-    cudaFree(W.ray_o); cudaFree(W.ray_d); cudaFree(W.tp); cudaFree(W.rad); cudaFree(W.pix);
-    for (int k = 0; k < WF_TAGS; ++k) cudaFree(W.q_shade[k]);
-    cudaFree(c->wf.q_extend[0]); cudaFree(c->wf.q_extend[1]); cudaFree(c->wf.q_free[0]); cudaFree(c->wf.q_free[1]);
-    cudaFree(W.counters); cudaFree(c->wf.owned_blocks);
+    dev_free(W.ray_o); dev_free(W.ray_d); dev_free(W.tp); dev_free(W.rad); dev_free(W.pix);
+    for (int k = 0; k < WF_TAGS; ++k) dev_free(W.q_shade[k]);
+    dev_free(c->wf.q_extend[0]); dev_free(c->wf.q_extend[1]); dev_free(c->wf.q_free[0]); dev_free(c->wf.q_free[1]);
+    dev_free(W.counters); dev_free(c->wf.owned_blocks);
     cudaFreeHost(c->wf.h_counters);
   }
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -146,6 +233,11 @@ extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
 int32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+uint64_t rt_trim_device_cache(void) {
+  DevCache& C = dev_cache();
+  std::lock_guard<std::mutex> lk(C.mu);
+  return (uint64_t)dev_trim_locked(C);
+}
 int32_t rt_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -208,7 +300,7 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs.list_n[k];
   d.seed_lo = (uint32_t)opts->seed;
   d.seed_hi = (uint32_t)(opts->seed >> 32);
-  if (cudaMalloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
+  if (dev_alloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
       cudaEventCreate(&c->ev1) != cudaSuccess) {
     std::string m = cudaGetErrorString(cudaGetLastError());
     free_camera(c);
@@ -276,25 +368,25 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
     const int n = slots_env > 0 ? slots_env : (1 << 22); // 4 Mi paths in flight, 80 B each
     WfBuffers& W = H.W;
     W.n_slots = n;
-    CU(cudaMalloc(&W.ray_o, (size_t)n * sizeof(F4)));
-    CU(cudaMalloc(&W.ray_d, (size_t)n * sizeof(F4)));
-    CU(cudaMalloc(&W.tp, (size_t)n * sizeof(F4)));
-    CU(cudaMalloc(&W.rad, (size_t)n * sizeof(F4)));
-    CU(cudaMalloc(&W.pix, (size_t)n * sizeof(U2)));
-    for (int k = 0; k < WF_TAGS; ++k) CU(cudaMalloc(&W.q_shade[k], (size_t)n * sizeof(int)));
+    CU(dev_alloc(&W.ray_o, (size_t)n * sizeof(F4)));
+    CU(dev_alloc(&W.ray_d, (size_t)n * sizeof(F4)));
+    CU(dev_alloc(&W.tp, (size_t)n * sizeof(F4)));
+    CU(dev_alloc(&W.rad, (size_t)n * sizeof(F4)));
+    CU(dev_alloc(&W.pix, (size_t)n * sizeof(U2)));
+    for (int k = 0; k < WF_TAGS; ++k) CU(dev_alloc(&W.q_shade[k], (size_t)n * sizeof(int)));
     for (int k = 0; k < 2; ++k) {
-      CU(cudaMalloc(&H.q_extend[k], (size_t)n * sizeof(int)));
-      CU(cudaMalloc(&H.q_free[k], (size_t)n * sizeof(int)));
+      CU(dev_alloc(&H.q_extend[k], (size_t)n * sizeof(int)));
+      CU(dev_alloc(&H.q_free[k], (size_t)n * sizeof(int)));
     }
-    CU(cudaMalloc(&W.counters, WFC_COUNT * sizeof(int)));
+    CU(dev_alloc(&W.counters, WFC_COUNT * sizeof(int)));
     CU(cudaMallocHost(&H.h_counters, WFC_COUNT * sizeof(int)));
     c->wf_ready = true;
   }
   if ((int)owned.size() > H.owned_capacity) {
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(H.owned_blocks);
+    dev_free(H.owned_blocks);
     H.owned_blocks = nullptr;
-    CU(cudaMalloc(&H.owned_blocks, std::max<size_t>(owned.size(), 1) * sizeof(int)));
+    CU(dev_alloc(&H.owned_blocks, std::max<size_t>(owned.size(), 1) * sizeof(int)));
     H.owned_capacity = (int)owned.size();
   }
   if (!owned.empty()) CU(cudaMemcpy(H.owned_blocks, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -328,9 +420,9 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     const size_t need_q = 1 + (size_t)P.tiles_x * P.tiles_y * 8; // queue head + one completion counter per 8x4 block
     if (need_q > c->queue_ints) {
       CU(cudaStreamSynchronize(c->stream));
-      cudaFree(c->d_queue);
+      dev_free(c->d_queue);
       c->d_queue = nullptr;
-      CU(cudaMalloc(&c->d_queue, need_q * sizeof(int)));
+      CU(dev_alloc(&c->d_queue, need_q * sizeof(int)));
       c->queue_ints = need_q;
     }
     // fixed-point radiance sums [H][W][4] u64, only when a pixel's samples are split over CTAs
@@ -338,9 +430,9 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     const size_t need_s = (P.chunks > 1 || wavefront) ? (size_t)4 * c->hs.image_width * c->hs.image_height : 0;
     if (need_s > c->scratch_elems) {
       CU(cudaStreamSynchronize(c->stream));
-      cudaFree(c->d_scratch);
+      dev_free(c->d_scratch);
       c->d_scratch = nullptr;
-      CU(cudaMalloc(&c->d_scratch, need_s * sizeof(unsigned long long)));
+      CU(dev_alloc(&c->d_scratch, need_s * sizeof(unsigned long long)));
       c->scratch_elems = need_s;
     }
     CU(cudaMemsetAsync(c->d_queue, 0, need_q * sizeof(int), c->stream));
@@ -395,9 +487,9 @@ static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb
   RenderParams P;
   rt_status st = clip_region(c, region, P);
   if (st != RT_OK) return st;
-  if (rgb8 && !c->d_rgb8) CU(cudaMalloc(&c->d_rgb8, npx * 3));
-  if (linear && !c->d_linear) CU(cudaMalloc(&c->d_linear, npx * 3 * sizeof(float)));
-  if (moments && !c->d_moments) CU(cudaMalloc(&c->d_moments, npx * 8 * sizeof(float)));
+  if (rgb8 && !c->d_rgb8) CU(dev_alloc(&c->d_rgb8, npx * 3));
+  if (linear && !c->d_linear) CU(dev_alloc(&c->d_linear, npx * 3 * sizeof(float)));
+  if (moments && !c->d_moments) CU(dev_alloc(&c->d_moments, npx * 8 * sizeof(float)));
   P.rgb8 = rgb8 ? c->d_rgb8 : nullptr;
   P.linear = linear ? c->d_linear : nullptr;
   P.moments = moments ? c->d_moments : nullptr;
@@ -478,10 +570,10 @@ rt_status rt_camera_trace_primary(rt_camera* c, const rt_region* region, int32_t
   RenderParams P;
   rt_status st = clip_region(c, region, P);
   if (st != RT_OK) return st;
-  if (!c->d_ids) CU(cudaMalloc(&c->d_ids, npx * 4));
-  if (!c->d_t) CU(cudaMalloc(&c->d_t, npx * 4));
-  if (!c->d_normal) CU(cudaMalloc(&c->d_normal, npx * 12));
-  if (!c->d_front) CU(cudaMalloc(&c->d_front, npx));
+  if (!c->d_ids) CU(dev_alloc(&c->d_ids, npx * 4));
+  if (!c->d_t) CU(dev_alloc(&c->d_t, npx * 4));
+  if (!c->d_normal) CU(dev_alloc(&c->d_normal, npx * 12));
+  if (!c->d_front) CU(dev_alloc(&c->d_front, npx));
   CU(launch_trace_primary(c->ds, P, c->d_ids, c->d_t, c->d_normal, c->d_front, c->stream));
   const int rw = P.x1 - P.x0, rh = P.y1 - P.y0;
   if (rw > 0 && rh > 0) {
@@ -506,7 +598,7 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
   CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
   const int blocks = sms * 16, iters = 2048;
   float* d = nullptr;
-  CU(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(float)));
+  CU(dev_alloc(&d, (size_t)blocks * 256 * sizeof(float)));
   cudaEvent_t a, b;
   CU(cudaEventCreate(&a));
   CU(cudaEventCreate(&b));
@@ -524,7 +616,7 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
-  cudaFree(d);
+  dev_free(d);
   *tflops = best;
   if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
   return RT_OK;

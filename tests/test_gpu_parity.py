@@ -406,3 +406,22 @@ def test_image_independent_of_chunking(gpu, monkeypatch):
     monkeypatch.delenv("RT_B200_CHUNKS")
     for im in imgs[1:]:
         assert np.array_equal(im["linear"], imgs[0]["linear"]) and np.array_equal(im["rgb8"], imgs[0]["rgb8"])
+
+
+# ------------------------------------------------------------------------------------------
+# device memory cache: create/destroy per image must not change results, trim gives memory back
+# ------------------------------------------------------------------------------------------
+def test_device_cache_reuse_and_trim(gpu):
+    from mcp_raytracer_b200 import trimDeviceCache
+    sd = SCENES["C2-cornell"]()
+    opts = {"width": 96, "samples": 40, "aTolerance": 0, "seed": 3}  # 40 spp on a small image: chunked, uses the accumulator
+    first = gpu_render(sd, opts)
+    trimDeviceCache()
+    for _ in range(3):  # buffers of the previous camera are handed out again (stale contents must not leak into the image)
+        again = gpu_render(sd, opts)
+        assert np.array_equal(first["rgb8"], again["rgb8"])
+        other = gpu_render(SCENES["C1-spheres"](), {"width": 120, "samples": 4, "aTolerance": 0})
+        assert other["stats"].pixels == other["rgb8"].shape[0] * other["rgb8"].shape[1]
+    assert trimDeviceCache() > 0
+    assert trimDeviceCache() == 0
+    assert np.array_equal(first["rgb8"], gpu_render(sd, opts)["rgb8"])
