@@ -167,6 +167,18 @@ class ClockSampler:
         return out
 
 
+def measured_traffic(workload, world, overridden):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the render kernel, per launch, from the committed
+    `ncu --set full` capture of this command (profiles/r01_bench_traffic.json); None when the run is not that one."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_traffic.json")))
+    except Exception:
+        return None
+    if overridden or t.get("workload") != workload or t.get("n_gpus") != world:
+        return None
+    return t.get("dram_bytes_total")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -369,7 +381,7 @@ def main():
         hbm_bytes = W * H * 3 + h2d  # compulsory traffic: scene once + RGB8 out
         roof = {
             "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None,
+            "traffic": measured_traffic(args.workload, world, overridden),
             "peak_source": f"FP32 FFMA microbenchmark in this run (rt_measure_fp32_peak): {fp32_peak:.1f} TFLOP/s per GPU at <= {sm_attr_mhz:.0f} MHz; "
                            "MEASURED_PEAKS.json holds HBM/bf16 peaks only",
             "flops_per_path": flops_per_path, "flops_model": "SURVEY.md §8d, event counts from the oracle walking the reference BVH",
