@@ -369,11 +369,13 @@ def main():
     except Exception:
         pass
     if not args.no_cpu_baseline:
-        c = cpu_reference_run(sd, ropts, target_seconds=args.cpu_seconds, threads=cpu_threads)
+        # the CPU baseline is reported at N=1 only; at N>1 a 1-second run still supplies the event counts of the flop model
+        c = cpu_reference_run(sd, ropts, target_seconds=args.cpu_seconds if world == 1 else 1.0, threads=cpu_threads)
         sample = c["sample"]
-        cpu = {"value": c["mpaths_per_s"], "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
-               "grays_per_s": c["grays_per_s"], "seconds": c["seconds"],
-               "note": "C++ restatement of the TypeScript reference (cannot run here); row strips, one per thread, like src/raytracer.ts:60-90"}
+        if world == 1:
+            cpu = {"value": c["mpaths_per_s"], "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
+                   "grays_per_s": c["grays_per_s"], "seconds": c["seconds"],
+                   "note": "C++ restatement of the TypeScript reference (cannot run here); row strips, one per thread, like src/raytracer.ts:60-90"}
         flops_per_path = algorithmic_flops(c["counters"], c["n_lights"], float(sd["camera"].get("aperture", 0))) / max(1, c["counters"]["paths"])
         kernel_s = (total_ms * 1e-3) / args.steps  # one render kernel per step (max over ranks)
         achieved = flops_per_path * paths_per_step / kernel_s / 1e12
@@ -394,7 +396,7 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": label + (" [OVERRIDDEN size: development run]" if overridden else ""), "image": f"{W}x{H}", "spp": ropts["samples"],
-                   "bvh": {1: "reference", 2: "sah", 3: "list"}.get(cam.info.bvh_kind), "integrator": "megakernel",
+                   "bvh": {1: "reference", 2: "sah", 3: "list"}.get(cam.info.bvh_kind), "integrator": {1: "megakernel", 2: "wavefront", 3: "sorted"}.get(cam.info.integrator_kind),
                    "partition": f"16x16 tiles, owner=(tx+ty)%{world}", "rng": "Philox4x32-10 keyed (pixel,sample), counter (block,bounce)",
                    "l2": "256 MiB memset between steps, outside the per-step CUDA-event pairs"},
         "grays_per_s": grays, "paths_per_step": paths_per_step, "rays_per_step": rays_per_step,

@@ -1,0 +1,29 @@
+"""Adaptive-sampling / render-mode renders (the reference's defaults: aTolerance 0.05, aBatch 10): image hash,
+stats and time, to compare kernel variants (RT_B200_OLD_PIXELS=1 selects the tile-synchronous kernel).
+usage: gpu_adaptive.py [width] [spp] [workloads...]"""
+import hashlib, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import bench
+from mcp_raytracer_b200 import createCameraFromSceneData
+width = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+spp = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+wls = sys.argv[3:] or ["C1", "C2", "C3", "C5"]
+for wl in wls:
+    label, kind, sopts, ropts = bench.WORKLOADS[wl]
+    sd = bench.make_scene(kind, sopts)
+    for extra in ({"aTolerance": 0.05, "aBatch": 10}, {"aTolerance": 0.01, "aBatch": 10}, {"aTolerance": 0.05, "mode": "samples"},
+                  {"aTolerance": 0, "mode": "bounces"}):
+        o = dict(ropts, **extra)
+        if width: o["width"] = width
+        if spp: o["samples"] = spp
+        with createCameraFromSceneData(sd, o) as cam:
+            rgb = np.zeros(cam.imageWidth * cam.imageHeight * 3, np.uint8)
+            best = None
+            for _ in range(2):
+                st = cam.render(rgb)
+                if best is None or st.deviceMs < best.deviceMs: best = st
+            print(wl, f"{cam.imageWidth}x{cam.imageHeight}@{o['samples']}", extra, hashlib.sha1(rgb.tobytes()).hexdigest()[:12], best.pixels,
+                  best.samples["total"], best.samples["min"], best.samples["max"], best.bounces["total"], best.rays,
+                  f"{best.deviceMs:.2f} ms {best.samples['total']/best.deviceMs/1e3:.0f} Mpaths/s")
