@@ -264,6 +264,38 @@ def test_adaptive_sampling_matches_oracle(gpu):  # camera.ts:348-368, :406
     assert gs.samples["total"] < 0.8 * gs.pixels * 100      # adaptive exit really saves samples
 
 
+@pytest.mark.parametrize("name,bvh", [("C2-cornell", "auto"), ("C3-weekend", "auto"), ("C4-rain", "auto"), ("default", "reference")])
+def test_adaptive_pixel_stream_regions_and_partitions(gpu, name, bvh):
+    """k_render_stream hands pixels to lanes in scheduling order; a pixel's samples stay in one lane and in order, so
+    the image and the per-pixel sample counts cannot depend on regions, partitions or which lane ran what."""
+    sd = SCENES[name]()
+    opts = {"width": 150, "samples": 48, "aTolerance": 0.05, "aBatch": 10, "seed": 8, "bvh": bvh}
+    whole = gpu_render(sd, opts, want_moments=True)
+    H, W = whole["rgb8"].shape[:2]
+    n = whole["moments"][..., 6]
+    assert n.min() >= 10 and n.max() <= 48 and float(n.sum()) == whole["stats"].samples["total"]
+    assert np.array_equal(gpu_render(sd, opts)["rgb8"], whole["rgb8"])  # deterministic
+    # 3-way tile partition inside a ragged region
+    reg = {"x": 7, "y": 9, "width": W - 20, "height": H - 15}
+    buf = np.full((H, W, 3), 77, np.uint8)
+    px = samples = 0
+    for k in range(3):
+        with createCameraFromSceneData(sd, {**opts, "partIndex": k, "partCount": 3}) as cam:
+            st = cam.renderRegion(buf, reg)
+            px += st.pixels
+            samples += st.samples["total"]
+    inside = np.zeros((H, W), bool)
+    inside[reg["y"]:reg["y"] + reg["height"], reg["x"]:reg["x"] + reg["width"]] = True
+    assert px == int(inside.sum()) and samples == int(n[inside].sum())
+    assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], whole["rgb8"][inside])
+
+
+def test_zero_samples_gives_black_image(gpu):  # while (pixel.samples < 0) never runs: colour/0 -> NaN -> 0 (camera.ts:406, :455-472)
+    g = gpu_render(SCENES["C2-cornell"](), {"width": 40, "samples": 0})
+    assert g["stats"].pixels == 1600 and g["stats"].samples["total"] == 0
+    assert not g["rgb8"].any()
+
+
 def test_render_modes(gpu):  # camera.ts:326-340
     sd = SCENES["C1-spheres"]()
     base = {"width": 96, "samples": 40, "aTolerance": 0.05, "seed": 2}

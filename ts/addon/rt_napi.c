@@ -118,12 +118,14 @@ static napi_value DestroyCamera(napi_env env, napi_callback_info info) {
   (void)info; napi_value u; napi_get_undefined(env, &u); return u;
 }
 static napi_value DeviceCount(napi_env env, napi_callback_info info) { (void)info; napi_value v; napi_create_int32(env, rt_device_count(), &v); return v; }
+/* device buffers of destroyed cameras are cached for the next createCamera; a long-lived MCP server can hand them back */
+static napi_value TrimDeviceCache(napi_env env, napi_callback_info info) { (void)info; napi_value v; napi_create_double(env, (double)rt_trim_device_cache(), &v); return v; }
 
 static napi_value Init(napi_env env, napi_value exports) {
   napi_property_descriptor d[] = {
     {"createCamera", 0, CreateCamera, 0, 0, 0, napi_default, 0}, {"renderRegion", 0, RenderRegion, 0, 0, 0, napi_default, 0},
     {"cameraInfo", 0, CameraInfo, 0, 0, 0, napi_default, 0}, {"destroyCamera", 0, DestroyCamera, 0, 0, 0, napi_default, 0},
-    {"deviceCount", 0, DeviceCount, 0, 0, 0, napi_default, 0},
+    {"deviceCount", 0, DeviceCount, 0, 0, 0, napi_default, 0}, {"trimDeviceCache", 0, TrimDeviceCache, 0, 0, 0, napi_default, 0},
   };
   napi_define_properties(env, exports, sizeof(d) / sizeof(d[0]), d);
   return exports;
