@@ -1244,7 +1244,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
     case BVH_SAH:
       // shallow trees: a whole traversal is a few node visits and interleaving only costs (measured on
       // the 480-sphere and 55-object scenes); deep trees: lanes diverge by 10x in visit count and win.
-      if (sorted_list && S.n_nodes < 4096) {
+      if (sorted_list && (S.n_nodes < 4096 || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
         return launch_persistent(k_render_sorted<BVH_SAH>, S, R, work, sms, st);

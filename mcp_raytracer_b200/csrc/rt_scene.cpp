@@ -617,7 +617,10 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   int kind = o->bvh;
   if (kind == RT_BVH_AUTO) {
     if (any_negative) kind = BVH_REFERENCE;      // inverted boxes are only meaningful in the reference topology
-    else if (n <= 64) kind = BVH_LIST; // measured: brute force over <= 64 shared-memory records beats a tree (55-object scene: 34 vs 50 ms)
+    // measured with the while-while tree walk (scripts/gpu_list_vs_sah.py, open spheres scene): brute force over
+    // shared-memory records wins up to ~17 objects, ties at 25, loses 35 % at 33 and 2x at 65; the closed
+    // 55-object layered/mixed box: SAH 103 ms vs LIST 109 ms.  Cornell (8 objects) is the LIST kernel's case.
+    else if (n <= 24) kind = BVH_LIST;
     else kind = BVH_SAH;
   }
   if (kind != BVH_REFERENCE && kind != BVH_SAH && kind != BVH_LIST) { err = "invalid bvh kind"; return RT_ERR_INVALID_ARGUMENT; }
