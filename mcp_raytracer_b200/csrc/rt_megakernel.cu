@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
   unsigned int* acc = s_acc[threadIdx.x >> 5];
-  int stack[64];
+  TravStack stack;
 
   unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
   int st_bmin = 0x7fffffff, st_bmax = 0;

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const Re
   } else {
     // persistent threads with a warp-level ray queue: lanes pull ray ids on demand
     const unsigned lane = threadIdx.x & 31u;
-    int stack[64];
+    TravStack stack;
     int id = 0, leaf_a = 0, leaf_b = 0;
     int st = ST_NONE;
     bool retired = false;
