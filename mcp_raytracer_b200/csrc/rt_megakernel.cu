@@ -1242,14 +1242,18 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       }
       return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
     case BVH_SAH:
-      // shallow trees: a whole traversal is a few node visits and interleaving only costs (measured on
-      // the 480-sphere and 55-object scenes); deep trees: lanes diverge by 10x in visit count and win.
-      if (sorted_list && (S.n_nodes < 4096 || no_trav)) {
+      // Whole-query while-while walk (k_render_pool) vs the resumable state machine (k_render_trav), rain scene
+      // at 1 k ... 100 k spheres (scripts/gpu_trav_threshold.py): 5.2 / 8.0 ms at 600 nodes, 14.5 / 17.5 at
+      // 4.8 k, 22.9 / 24.9 at 11.8 k, 33.7 / 33.8 at 28.6 k, 48.0 / 44.4 at 63.7 k nodes: the votes and state
+      // switches of the state machine only pay once lanes diverge by hundreds of node visits.
+      constexpr int kTravNodes = 32768;
+      if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
         return launch_persistent(k_render_sorted<BVH_SAH>, S, R, work, sms, st);
       }
-      if (no_trav || S.n_nodes < 4096) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
+      static const bool trav_always = getenv("RT_B200_TRAV_ALWAYS") != nullptr;
+      if (!trav_always && (no_trav || S.n_nodes < kTravNodes)) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
       return launch_persistent(k_render_trav, S, R, work, sms, st);
     default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);
   }

@@ -408,6 +408,31 @@ def test_sorted_integrator_equals_megakernel(gpu, name, width, spp, bvh):
     assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], a["rgb8"][inside])
 
 
+def test_deep_tree_state_machine_kernel(gpu):
+    """Trees above 32 k nodes run k_render_trav (resumable traversal interleaved with shading): same image as the
+    wavefront integrator (its own extend kernel) and as the union of a 3-way partition; primary hits vs the oracle."""
+    sd = generateRainSceneData({"count": 60000, "seed": 2, "sphereRadius": 0.012})
+    opts = {"width": 160, "samples": 6, "aTolerance": 0, "seed": 13}
+    with createCameraFromSceneData(sd, opts) as cam:
+        assert cam.info.n_bvh_nodes > 32768 and cam.info.bvh_kind == 2
+        ids, t, _, _ = cam.tracePrimary()
+    a = gpu_render(sd, {**opts, "integrator": "megakernel"})
+    b = gpu_render(sd, {**opts, "integrator": "wavefront"})
+    assert np.array_equal(a["rgb8"], b["rgb8"]) and np.array_equal(a["linear"], b["linear"])
+    assert (a["stats"].samples, a["stats"].bounces, a["stats"].rays) == (b["stats"].samples, b["stats"].bounces, b["stats"].rays)
+    H, W = a["rgb8"].shape[:2]
+    buf = np.zeros((H, W, 3), np.uint8)
+    for k in range(3):
+        with createCameraFromSceneData(sd, {**opts, "partIndex": k, "partCount": 3}) as cam:
+            cam.render(buf)
+    assert np.array_equal(buf, a["rgb8"])
+    # primary visibility against the oracle walking the reference's own tree (≈ 1 s at this size)
+    oids, ot, _, _ = ob.OracleCamera(sd, opts).trace_primary()
+    assert np.array_equal(ids, oids)
+    hit = oids >= 0
+    assert np.all(np.abs(t[hit] - ot[hit]) <= 1e-4 * np.abs(ot[hit]))
+
+
 def test_wavefront_region_and_partition(gpu):
     sd = SCENES["C2-cornell"]()
     opts = {"width": 100, "samples": 8, "aTolerance": 0, "seed": 9}
