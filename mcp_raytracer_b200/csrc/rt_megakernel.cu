@@ -1223,6 +1223,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
   static const bool env_sorted = getenv("RT_B200_SORTED") != nullptr;
   const bool sorted_list = env_sorted || R.sorted;
+  constexpr int kTravNodes = 32768; // see case BVH_SAH
   switch (S.bvh_kind) {
     case BVH_LIST:
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
@@ -1246,7 +1247,6 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       // at 1 k ... 100 k spheres (scripts/gpu_trav_threshold.py): 5.2 / 8.0 ms at 600 nodes, 14.5 / 17.5 at
       // 4.8 k, 22.9 / 24.9 at 11.8 k, 33.7 / 33.8 at 28.6 k, 48.0 / 44.4 at 63.7 k nodes: the votes and state
       // switches of the state machine only pay once lanes diverge by hundreds of node visits.
-      constexpr int kTravNodes = 32768;
       if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
