@@ -845,7 +845,6 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
     int st = ST_NONE;
     bool retired = false, fresh = false;
     Trav tv{-1, 0, CUDART_INF_F, -1};
-    int leaf_a = 0, leaf_b = 0; // postponed leaves of a lane in ST_LEAF
     BoxPre bp{mk3(0, 0, 0), mk3(0, 0, 0)};
     Rng g;
 
@@ -899,23 +898,23 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
         }
       }
 
-      // ---- traversal phase: converged rounds of inner-node visits and of leaf intersections
-      //      (while-while with postponed leaves); each round serves the larger of the two groups ----
+      // ---- traversal phase, in bursts: a lane walks up to R.trav_burst inner nodes until it holds a leaf
+      //      (while-while), the warp reconverges at the end of that loop and intersects the leaves together.
+      //      One vote per burst; the phase ends when few lanes still traverse and others have work waiting.
+      //      (Two votes per node visit with separate inner / leaf rounds measured 171 ms on the 100 k-sphere
+      //      scene at 8 spp; bursts of 2 / 4 / 8 / 16: 138 / 128 / 127 / 140 ms.) ----
       for (;;) {
-        const unsigned ti = __ballot_sync(0xffffffffu, st == ST_TRACE);
-        const unsigned tl = __ballot_sync(0xffffffffu, st == ST_LEAF);
-        if ((ti | tl) == 0) break;
-        if (__popc(ti | tl) <= R.trav_min_lanes) {
+        const unsigned tt = __ballot_sync(0xffffffffu, st == ST_TRACE);
+        if (tt == 0) break;
+        if (__popc(tt) <= R.trav_min_lanes) {
           // lanes that could do something else: shade a finished ray, start a bounce, take a new pair
           if (__any_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired))) break;
         }
-        if (__popc(ti) >= __popc(tl)) {
-          if (st == ST_TRACE) {
-            trav_inner(S, bp, tv, stack, leaf_a, leaf_b);
-            st = leaf_a != 0 ? ST_LEAF : (tv.cur >= 0 ? ST_TRACE : ST_HIT);
-          }
-        } else if (st == ST_LEAF) {
-          trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
+        if (st == ST_TRACE) {
+          int steps = 0, leaf_a = 0, leaf_b = 0;
+#pragma unroll 1 // unrolled copies of the node visit cost more instruction cache than they save
+          while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
+          if (leaf_a != 0) trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
@@ -1223,7 +1222,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
   static const bool env_sorted = getenv("RT_B200_SORTED") != nullptr;
   const bool sorted_list = env_sorted || R.sorted;
-  constexpr int kTravNodes = 32768; // see case BVH_SAH
+  constexpr int kTravNodes = 4096; // see case BVH_SAH
   switch (S.bvh_kind) {
     case BVH_LIST:
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
@@ -1243,10 +1242,10 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       }
       return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
     case BVH_SAH:
-      // Whole-query while-while walk (k_render_pool) vs the resumable state machine (k_render_trav), rain scene
-      // at 1 k ... 100 k spheres (scripts/gpu_trav_threshold.py): 5.2 / 8.0 ms at 600 nodes, 14.5 / 17.5 at
-      // 4.8 k, 22.9 / 24.9 at 11.8 k, 33.7 / 33.8 at 28.6 k, 48.0 / 44.4 at 63.7 k nodes: the votes and state
-      // switches of the state machine only pay once lanes diverge by hundreds of node visits.
+      // Whole-query while-while walk (k_render_pool) vs traversal bursts interleaved with shading (k_render_trav),
+      // rain scene at 1 k ... 50 k spheres (scripts/gpu_trav_threshold.py): 5.2 / 6.9 ms at 600 nodes, 8.7 / 9.9
+      // at 1.7 k, 11.3 / 12.0 at 2.8 k, 14.5 / 14.4 at 4.8 k, 22.9 / 19.9 at 11.8 k, 33.7 / 26.1 at 28.6 k nodes:
+      // regenerating paths mid-traversal pays once lanes diverge by many node visits.
       if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;

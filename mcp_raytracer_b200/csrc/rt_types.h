@@ -122,6 +122,7 @@ struct RenderParams {
   int* queue;                  // [0] = next work item
   int* tile_done;              // [8x4 blocks] finished chunks per block
   int trav_min_lanes;          // k_render_trav: leave the traversal phase when <= this many lanes still traverse
+  int trav_burst;              // k_render_trav: inner-node visits a lane may do between two votes
   int sorted;                  // use k_render_sorted (CTA-wide sort of hits by material class) where it exists
 };
 // ---- wavefront integrator (rt_wavefront.cuh): path pool + queues in HBM ----

@@ -219,21 +219,19 @@ __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const Re
       wf_bin(S, W, st == ST_HIT, id, tv.tbest, tv.sbest);
       if (st == ST_HIT) st = ST_NONE;
       if (__all_sync(0xffffffffu, st == ST_NONE && retired)) break;
-      // converged rounds of inner-node visits / leaf intersections until few lanes are left
+      // traversal bursts (see k_render_trav) until few lanes are left
       for (;;) {
-        const unsigned ti = __ballot_sync(0xffffffffu, st == ST_TRACE);
-        const unsigned tl = __ballot_sync(0xffffffffu, st == ST_LEAF);
-        if ((ti | tl) == 0) break;
-        if (__popc(ti | tl) <= R.trav_min_lanes) {
+        const unsigned tt = __ballot_sync(0xffffffffu, st == ST_TRACE);
+        if (tt == 0) break;
+        if (__popc(tt) <= R.trav_min_lanes) {
           if (__any_sync(0xffffffffu, st == ST_HIT || (st == ST_NONE && !retired))) break;
         }
-        if (__popc(ti) >= __popc(tl)) {
-          if (st == ST_TRACE) {
-            trav_inner(S, bp, tv, stack, leaf_a, leaf_b);
-            st = leaf_a != 0 ? ST_LEAF : (tv.cur >= 0 ? ST_TRACE : ST_HIT);
-          }
-        } else if (st == ST_LEAF) {
-          trav_leaves(S, ray, bp, tv, leaf_a, leaf_b);
+        if (st == ST_TRACE) {
+          int steps = 0;
+          leaf_a = 0;
+#pragma unroll 1
+          while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
+          if (leaf_a != 0) trav_leaves(S, ray, bp, tv, leaf_a, leaf_b);
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
