@@ -903,6 +903,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
       //      One vote per burst; the phase ends when few lanes still traverse and others have work waiting.
       //      (Two votes per node visit with separate inner / leaf rounds measured 171 ms on the 100 k-sphere
       //      scene at 8 spp; bursts of 2 / 4 / 8 / 16: 138 / 128 / 127 / 140 ms.) ----
+      //      Keeping the leaves of a burst parked until they outnumber the traversing lanes (bursts + the old
+      //      ST_LEAF rounds) was measured too: 136-139 ms against 126-129 ms.
       for (;;) {
         const unsigned tt = __ballot_sync(0xffffffffu, st == ST_TRACE);
         if (tt == 0) break;
