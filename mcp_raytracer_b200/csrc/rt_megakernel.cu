@@ -816,11 +816,10 @@ __global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, con
 
 // =========================================================================================
 // k_render_trav — fixed spp, default mode, SAH trees: traversal interleaved with shading.
-// Lane states: NONE (needs a pair) -> BEGIN (bounce not started) -> TRACE (mid-traversal) ->
-// LEAF (leaf children of the last node wait to be intersected) -> TRACE ... -> HIT (closest hit known,
-// not shaded) -> BEGIN | NONE.
+// Lane states: NONE (needs a pair) -> BEGIN (bounce not started) -> TRACE (mid-traversal, advanced in
+// bursts) -> HIT (closest hit known, not shaded) -> BEGIN | NONE.
 // =========================================================================================
-enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3, ST_LEAF = 4 };
+enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3 };
 
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevScene S, const RenderParams R) {
   __shared__ unsigned int s_acc[8][32 * 9];
@@ -1028,7 +1027,9 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
   int i = 0, j = 0, samples = 0;
   V3 color = mk3(0, 0, 0);
   unsigned int bounces_sum = 0;
-  double sum_ill = 0, sum_ill2 = 0;
+  double sum_ill = 0, sum_ill2 = 0; // PixelStats.sumIll / sumIll2 up to the last check
+  float b_ill = 0, b_ill2 = 0;      // ... plus the current batch (<= aBatch samples) in FP32
+  int countdown = 1;                // samples until the next convergence check
   float m2x = 0, m2y = 0, m2z = 0;
   PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
   Rng g;
@@ -1061,6 +1062,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         samples = 0; bounces_sum = 0;
         color = mk3(0, 0, 0);
         sum_ill = 0; sum_ill2 = 0;
+        b_ill = b_ill2 = 0.f;
+        countdown = cam.a_batch;
         m2x = m2y = m2z = 0;
       }
     }
@@ -1081,10 +1084,10 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         bounces_sum += (unsigned)ps.bounces;
         t_bmin = min(t_bmin, ps.bounces);
         t_bmax = max(t_bmax, ps.bounces);
-        if (cam.adaptive) {
-          double il = 0.299 * (double)ps.radiance.x + 0.587 * (double)ps.radiance.y + 0.114 * (double)ps.radiance.z;
-          sum_ill += il;
-          sum_ill2 += il * il;
+        if (cam.adaptive) { // illuminance (vec3.ts:239-242); FP32 partial sums of one batch, folded into FP64 at the check
+          const float il = fmaf(0.299f, ps.radiance.x, fmaf(0.587f, ps.radiance.y, 0.114f * ps.radiance.z));
+          b_ill += il;
+          b_ill2 = fmaf(il, il, b_ill2);
         }
         if (R.moments) {
           m2x = fmaf(ps.radiance.x, ps.radiance.x, m2x);
@@ -1094,7 +1097,16 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         need_path = true;
         // while (pixel.samples < samples && !pixelConverged(pixel)) — camera.ts:406, evaluated for the next sample
         stop = samples >= cam.samples;
-        if (!stop && cam.adaptive && samples >= 2 && (samples % cam.a_batch) == 0) { // camera.ts:348-368
+        // the check runs when samples % aBatch == 0 (camera.ts:348-368): a countdown instead of a division per sample
+        bool check = false;
+        if (cam.adaptive && --countdown == 0) {
+          countdown = cam.a_batch;
+          sum_ill += (double)b_ill;
+          sum_ill2 += (double)b_ill2;
+          b_ill = b_ill2 = 0.f;
+          check = samples >= 2;
+        }
+        if (!stop && check) {
           double n = (double)samples;
           double mean = sum_ill / n;
           double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
