@@ -46,6 +46,10 @@ WORKLOADS = {
            {"width": 3840, "samples": 64, "aTolerance": 0}),
     "C5": ("layered/mixed-material scene 2048x2048 @256spp (BASELINE configs[4])", "layered", {},
            {"width": 2048, "samples": 256, "aTolerance": 0}),
+    # what `benchmark.ts --rain 100000` renders: the generator's default radius 0.05 exceeds the cell spacing, so
+    # the spheres overlap massively; reported next to C4, not a BASELINE config of its own
+    "C4r": ("rain-scene 100k spheres, default radius 0.05, 3840x2160 @64spp", "rain", {"count": 100000, "seed": 1},
+            {"width": 3840, "samples": 64, "aTolerance": 0}),
 }
 
 

@@ -1121,6 +1121,145 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
 }
 
 // =========================================================================================
+// k_render_stream_trav — k_render_stream for deep SAH trees: the pixel stream of k_render_stream with the
+// resumable traversal of k_render_trav (bursts interleaved with shading), so a lane whose ray finished
+// early shades, takes its next sample or its next pixel while the others still walk the tree.  Per-pixel
+// arithmetic and its order are those of k_render_stream: identical output.
+// =========================================================================================
+__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const DevScene S, const RenderParams R) {
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
+  const int n_items = R.tiles_x * R.tiles_y * 8; // 8x4 blocks, eight per 16x16 tile
+  TravStack stack;
+
+  int blk_x0 = 0, blk_y0 = 0, cursor = 32; // the warp's pixel stream (warp-uniform)
+  bool queue_empty = false;
+  bool have_px = false; // this lane's pixel: PixelStats (renderStats.ts:67-88)
+  int i = 0, j = 0, samples = 0;
+  V3 color = mk3(0, 0, 0);
+  unsigned int bounces_sum = 0;
+  double sum_ill = 0, sum_ill2 = 0;
+  float b_ill = 0, b_ill2 = 0;
+  int countdown = 1;
+  float m2x = 0, m2y = 0, m2z = 0;
+  PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0}; // this lane's path
+  Rng g;
+  int st = ST_NONE;
+  bool fresh = false;
+  Trav tv{-1, 0, CUDART_INF_F, -1};
+  BoxPre bp{mk3(0, 0, 0), mk3(0, 0, 0)};
+  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0, t_rays = 0;
+  int t_smin = 0x7fffffff, t_smax = 0, t_bmin = 0x7fffffff, t_bmax = 0;
+
+  auto finish_pixel = [&]() {
+    stream_write_pixel(R.rgb8, R.linear, R.moments, cam.width, cam.mode, cam.depth, cam.samples, i, j, samples, bounces_sum, color.x,
+                       color.y, color.z, m2x, m2y, m2z);
+    ++t_pixels;
+    t_samples += (unsigned)samples;
+    t_bounces += bounces_sum;
+    t_smin = min(t_smin, samples);
+    t_smax = max(t_smax, samples);
+    have_px = false;
+  };
+  // pixel.add(rayColor, bounces, useAdaptiveSampling) + the loop condition of camera.ts:406 for the next sample
+  auto end_sample = [&]() {
+    color = color + ps.radiance;
+    ++samples;
+    bounces_sum += (unsigned)ps.bounces;
+    t_bmin = min(t_bmin, ps.bounces);
+    t_bmax = max(t_bmax, ps.bounces);
+    if (cam.adaptive) {
+      const float il = fmaf(0.299f, ps.radiance.x, fmaf(0.587f, ps.radiance.y, 0.114f * ps.radiance.z));
+      b_ill += il;
+      b_ill2 = fmaf(il, il, b_ill2);
+    }
+    if (R.moments) {
+      m2x = fmaf(ps.radiance.x, ps.radiance.x, m2x);
+      m2y = fmaf(ps.radiance.y, ps.radiance.y, m2y);
+      m2z = fmaf(ps.radiance.z, ps.radiance.z, m2z);
+    }
+    bool stop = samples >= cam.samples;
+    bool check = false;
+    if (cam.adaptive && --countdown == 0) {
+      countdown = cam.a_batch;
+      sum_ill += (double)b_ill;
+      sum_ill2 += (double)b_ill2;
+      b_ill = b_ill2 = 0.f;
+      check = samples >= 2;
+    }
+    if (!stop && check) { // camera.ts:348-368
+      double n = (double)samples;
+      double mean = sum_ill / n;
+      double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
+      if (var <= 0.0 || var != var) stop = true;
+      else stop = 1.96 * sqrt(var) / sqrt(n) <= (double)cam.a_tol * mean;
+    }
+    if (stop) { finish_pixel(); st = ST_NONE; }
+    else { st = ST_BEGIN; fresh = true; }
+  };
+
+  for (;;) {
+    // ---- lanes without a pixel take the next pixels of the stream ----
+    const unsigned want = __ballot_sync(full, st == ST_NONE && !have_px);
+    if (want != 0u) {
+      const StreamTake tk = stream_take(want, cursor, blk_x0, blk_y0, queue_empty, R.queue, n_items, R.tiles_x, R.x0, R.y0, R.x1,
+                                        R.y1, R.part_index, R.part_count, lane);
+      cursor = tk.cursor; blk_x0 = tk.blk_x0; blk_y0 = tk.blk_y0; queue_empty = tk.queue_empty != 0;
+      if (tk.got) {
+        i = tk.i; j = tk.j;
+        have_px = true;
+        samples = 0; bounces_sum = 0;
+        color = mk3(0, 0, 0);
+        sum_ill = 0; sum_ill2 = 0;
+        b_ill = b_ill2 = 0.f;
+        countdown = cam.a_batch;
+        m2x = m2y = m2z = 0;
+        if (cam.samples <= 0) finish_pixel(); // while (0 < 0): the pixel gets no sample at all
+        else { st = ST_BEGIN; fresh = true; }
+      }
+    }
+    if (__all_sync(full, st == ST_NONE && !have_px)) break; // stream exhausted and every pixel written
+
+    // ---- shading phase: finish the bounce of lanes whose ray is done, start the next bounce / sample ----
+    if (st == ST_HIT) {
+      if (path_post<BVH_SAH>(S, nullptr, mw, ps, g, tv.tbest, tv.sbest)) end_sample();
+      else st = ST_BEGIN;
+    }
+    if (st == ST_BEGIN) {
+      const uint32_t pixel = (uint32_t)j * (uint32_t)cam.width + (uint32_t)i;
+      if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
+      g.begin(pixel, (uint32_t)samples, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi);
+      if (fresh) { ps.ray = camera_ray(cam, i, j, g, true); fresh = false; }
+      if (path_pre(cam, ps, g)) end_sample(); // ended by the depth limit or the roulette: nothing to trace
+      else {
+        ++t_rays;
+        trav_begin(S, ps.ray, tv);
+        bp = box_precompute(ps.ray);
+        st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
+      }
+    }
+
+    // ---- traversal bursts (see k_render_trav) ----
+    for (;;) {
+      const unsigned tt = __ballot_sync(full, st == ST_TRACE);
+      if (tt == 0) break;
+      if (__popc(tt) <= R.trav_min_lanes) {
+        if (__any_sync(full, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !(queue_empty && cursor >= 32)))) break;
+      }
+      if (st == ST_TRACE) {
+        int steps = 0, leaf_a = 0, leaf_b = 0;
+#pragma unroll 1
+        while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
+        if (leaf_a != 0) trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
+        st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
+      }
+    }
+  }
+  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, t_rays, t_bmin, t_bmax);
+}
+
+// =========================================================================================
 // primary visibility (parity hook): pixel-centre rays, no jitter, no defocus
 // =========================================================================================
 template <int KIND>
@@ -1223,10 +1362,14 @@ static cudaError_t launch_wq(const DevScene& S, const RenderParams& R, long long
 cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st) {
   if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
   const long long tiles = (long long)R.tiles_x * R.tiles_y;
+  constexpr int kTravNodes = 4096; // tree size from which resumable traversal beats the whole-query walk (see case BVH_SAH below)
   if (render_needs_full(S, R)) {
+    static const bool no_stream_trav = getenv("RT_B200_NO_STREAM_TRAV") != nullptr; // development switch
     switch (S.bvh_kind) {
       case BVH_LIST: return launch_persistent(k_render_stream<BVH_LIST>, S, R, tiles, sms, st);
-      case BVH_SAH: return launch_persistent(k_render_stream<BVH_SAH>, S, R, tiles, sms, st);
+      case BVH_SAH:
+        if (S.n_nodes >= kTravNodes && !no_stream_trav) return launch_persistent(k_render_stream_trav, S, R, tiles, sms, st);
+        return launch_persistent(k_render_stream<BVH_SAH>, S, R, tiles, sms, st);
       default: return launch_persistent(k_render_stream<BVH_REFERENCE>, S, R, tiles, sms, st);
     }
   }
@@ -1236,7 +1379,6 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
   static const bool env_sorted = getenv("RT_B200_SORTED") != nullptr;
   const bool sorted_list = env_sorted || R.sorted;
-  constexpr int kTravNodes = 4096; // see case BVH_SAH
   switch (S.bvh_kind) {
     case BVH_LIST:
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
