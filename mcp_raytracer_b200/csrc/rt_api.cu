@@ -444,8 +444,10 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     {
       static const int trav_env = getenv("RT_B200_TRAV_MIN") ? atoi(getenv("RT_B200_TRAV_MIN")) : -1; // development override
       static const int burst_env = getenv("RT_B200_TRAV_BURST") ? atoi(getenv("RT_B200_TRAV_BURST")) : -1; // development override
-      P.trav_min_lanes = trav_env >= 0 ? trav_env : 16; // swept 0..24 on the 100k-sphere scene: 12-16 is the plateau
-      P.trav_burst = burst_env >= 1 ? burst_env : 6;    // swept 2..16: 4-8 is the plateau
+      // swept on the 100k-sphere scene with the 4-wide tree (8 spp, ms): burst 4: min 4/8/10/12/16/20 = 118/116/116/118/124/133;
+      // burst 6: 123/119/119/120/124/131; burst 2 and 8 are worse at every setting
+      P.trav_min_lanes = trav_env >= 0 ? trav_env : 8;
+      P.trav_burst = burst_env >= 1 ? burst_env : 4;
     }
     P.sorted = c->integrator == RT_INTEGRATOR_SORTED;
     P.queue = c->d_queue;

@@ -912,10 +912,11 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
           if (__any_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired))) break;
         }
         if (st == ST_TRACE) {
-          int steps = 0, leaf_a = 0, leaf_b = 0;
+          int steps = 0;
+          TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1 // unrolled copies of the node visit cost more instruction cache than they save
-          while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
-          if (leaf_a != 0) trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
+          while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
+          if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
@@ -1248,10 +1249,11 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
         if (__any_sync(full, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !(queue_empty && cursor >= 32)))) break;
       }
       if (st == ST_TRACE) {
-        int steps = 0, leaf_a = 0, leaf_b = 0;
+        int steps = 0;
+          TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1
-        while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
-        if (leaf_a != 0) trav_leaves(S, ps.ray, bp, tv, leaf_a, leaf_b);
+        while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
+        if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
         st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
       }
     }
@@ -1362,7 +1364,7 @@ static cudaError_t launch_wq(const DevScene& S, const RenderParams& R, long long
 cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st) {
   if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
   const long long tiles = (long long)R.tiles_x * R.tiles_y;
-  constexpr int kTravNodes = 4096; // tree size from which resumable traversal beats the whole-query walk (see case BVH_SAH below)
+  constexpr int kTravNodes = 16384; // tree size from which resumable traversal beats the whole-query walk (see case BVH_SAH below)
   if (render_needs_full(S, R)) {
     static const bool no_stream_trav = getenv("RT_B200_NO_STREAM_TRAV") != nullptr; // development switch
     switch (S.bvh_kind) {
@@ -1399,9 +1401,10 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
     case BVH_SAH:
       // Whole-query while-while walk (k_render_pool) vs traversal bursts interleaved with shading (k_render_trav),
-      // rain scene at 1 k ... 50 k spheres (scripts/gpu_trav_threshold.py): 5.2 / 6.9 ms at 600 nodes, 8.7 / 9.9
-      // at 1.7 k, 11.3 / 12.0 at 2.8 k, 14.5 / 14.4 at 4.8 k, 22.9 / 19.9 at 11.8 k, 33.7 / 26.1 at 28.6 k nodes:
-      // regenerating paths mid-traversal pays once lanes diverge by many node visits.
+      // rain scene at 1 k ... 100 k spheres with the 4-wide tree (scripts/gpu_trav_threshold.py; n_nodes counts
+      // 64-byte slots): 4.9 / 7.8 ms at 0.6 k, 8.0 / 11.1 at 1.8 k, 12.6 / 15.0 at 4.9 k, 19.1 / 19.5 at 11.8 k,
+      // 27.3 / ~24 at 28.6 k, 37.8 / 30.2 at 63.7 k: regenerating paths mid-traversal pays once lanes diverge by
+      // many node visits.
       if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;

@@ -504,6 +504,46 @@ struct Flattener {
     nd.right = r >= 0 ? emit(r, depth + 1) : kEmptyRef;
     S.nodes[idx] = nd;
   }
+
+  // SAH trees are flattened 4 wide (WideNode, 128 B = two Node slots): the binary tree is collapsed by
+  // replacing the internal child with the largest box by its two children until a node has four children or
+  // only leaves.  Half the dependent node fetches per ray; the deep-tree kernels wait on those fetches.
+  // Returns the wide-node index (in units of WideNode) of build node bi (internal), or emits a single-leaf root.
+  int emit_wide(int bi, int depth) {
+    max_depth = std::max(max_depth, depth);
+    int c[4], nc = 0;
+    if (pool[bi].leaf) c[nc++] = bi; // a tree that is one leaf: root with a single leaf child
+    else { c[nc++] = pool[bi].left; c[nc++] = pool[bi].right; }
+    while (nc < 4) {
+      int pick = -1;
+      double best = -1;
+      for (int k = 0; k < nc; ++k) {
+        if (pool[c[k]].leaf) continue;
+        const double a = SahBuilder::area(pool[c[k]].box);
+        if (a > best) { best = a; pick = k; }
+      }
+      if (pick < 0) break;
+      const int l = pool[c[pick]].left, r = pool[c[pick]].right;
+      for (int k = nc; k > pick + 1; --k) c[k] = c[k - 1]; // keep the order: the two children take the parent's place
+      c[pick] = l;
+      c[pick + 1] = r;
+      ++nc;
+    }
+    const int idx = (int)S.nodes.size() / 2;
+    S.nodes.emplace_back();
+    S.nodes.emplace_back();
+    WideNode w;
+    for (int k = 0; k < 4; ++k) {
+      const Box b = k < nc ? pool[c[k]].box : empty_box();
+      std::memcpy(w.box[k], b.mn, 12);
+      std::memcpy(w.box[k] + 3, b.mx, 12);
+      w.ref[k] = kEmptyRef;
+      w.pad[k] = 0;
+    }
+    for (int k = 0; k < nc; ++k) w.ref[k] = pool[c[k]].leaf ? leaf_ref(pool[c[k]]) : emit_wide(c[k], depth + 1);
+    std::memcpy(&S.nodes[2 * (size_t)idx], &w, sizeof(w));
+    return idx;
+  }
 };
 
 } // namespace
@@ -697,9 +737,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
       pool.reserve(bounded.size());
       int root = SahBuilder::build_all(P, bounded, pool);
       lap("sah build");
-      S.nodes.emplace_back();
-      if (pool[root].leaf) fl.fill_pair(0, root, -1, 0);
-      else fl.fill_pair(0, pool[root].left, pool[root].right, 0);
+      fl.emit_wide(root, 0); // wide node 0 = the root
     }
   }
   lap("flatten");

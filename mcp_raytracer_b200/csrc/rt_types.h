@@ -1,7 +1,8 @@
 // rt_types.h — POD layouts shared by the host scene compiler and the sm_100a kernels.
 //
 // Data layout in HBM (all arrays 16-byte aligned, read-only during a render):
-//   nodes   [n_nodes]  4 x float4 = 64 B   two child boxes + two child refs (pair layout)
+//   nodes   [n_nodes]  4 x float4 = 64 B   REFERENCE trees: two child boxes + two child refs (pair layout, Node);
+//                                          SAH trees: 4-wide nodes of two slots each (WideNode, 128 B)
 //   p0      [n_slots]  float4              sphere: (cx,cy,cz,r) | planar: (nx,ny,nz,D)
 //   p1,p2   [n_slots]  float4              planar only: (A.xyz, q.A) and (B.xyz, q.B) with
 //                                          A = v x w, B = w x u  =>  alpha = p.A - q.A,
@@ -52,6 +53,14 @@ struct alignas(16) Node { // 64 B
   int left, right;
   int flags; // bit0/bit1: left/right subtree holds an inverted box => test it with the reference's per-axis rule
   int pad1;
+};
+
+// SAH trees: four children per node (the binary tree collapsed, rt_scene.cpp), 128 B = two Node slots.
+// box[k] = (min.xyz, max.xyz) of child k, ref[k] as above; unused children: inverted box + kEmptyRef.
+struct alignas(16) WideNode {
+  float box[4][6];
+  int ref[4];
+  int pad[4];
 };
 
 struct alignas(16) ExactPrim { // 96 B

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const Re
     // persistent threads with a warp-level ray queue: lanes pull ray ids on demand
     const unsigned lane = threadIdx.x & 31u;
     TravStack stack;
-    int id = 0, leaf_a = 0, leaf_b = 0;
+    int id = 0;
     int st = ST_NONE;
     bool retired = false;
     Ray ray{mk3(0, 0, 0), mk3(0, 0, 1)};
@@ -228,10 +228,10 @@ __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const Re
         }
         if (st == ST_TRACE) {
           int steps = 0;
-          leaf_a = 0;
+          TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1
-          while (tv.cur >= 0 && leaf_a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, leaf_a, leaf_b); ++steps; }
-          if (leaf_a != 0) trav_leaves(S, ray, bp, tv, leaf_a, leaf_b);
+          while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
+          if (lv.a != 0) trav_leaves(S, ray, bp, tv, lv);
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
