@@ -13,14 +13,17 @@
 // pixel in exact 64-bit fixed point, so the image does not depend on which lane took which sample, on
 // the chunking or on the number of GPUs.
 //   * k_render_pool<LIST>: tiny scenes, all primitives in shared memory, converged brute-force loop.
-//   * k_render_trav (SAH trees): BVH traversal is a resumable state machine; a warp alternates
-//     between traversal steps (one node visit for every lane that is mid-ray) and shading/regeneration
-//     for the lanes whose ray finished, switching when too few lanes still traverse — the warp never
-//     waits for its longest traversal with idle lanes.
+//   * k_render_pool<SAH>: small and medium trees, one whole while-while tree walk per iteration.
+//   * k_render_trav (big SAH trees): traversal is resumable; a warp alternates traversal bursts (a few
+//     node visits for every lane that is mid-ray) with shading/regeneration for the lanes whose ray
+//     finished, switching when few lanes still traverse — the warp never waits for its longest
+//     traversal with idle lanes.
+//   * k_render_sorted (SORTED integrator): CTA-wide counting sort of the hits by material class between
+//     the trace and the shade phase.
 //
-// k_render_stream (adaptive sampling / render modes / moments): a lane owns one pixel at a time and runs the
-// reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule requires; lanes pull
-// the next pixel from their warp's stream when theirs stops.
+// k_render_stream / k_render_stream_trav (adaptive sampling / render modes / moments): a lane owns one pixel
+// at a time and runs the reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule
+// requires; lanes pull the next pixel from their warp's stream when theirs stops.
 //
 // All path state lives in registers; HBM sees the scene reads (L1/L2 resident), 24 B of atomics per
 // (pixel, chunk) when chunks > 1, and 3 bytes per pixel of output.

@@ -742,7 +742,9 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   }
   lap("flatten");
   S.max_depth = fl.max_depth;
-  if (S.max_depth > 60) { err = "BVH too deep"; return RT_ERR_UNSUPPORTED; }
+  // device stacks: 64 entries for the binary REFERENCE walk (one push per level), 128 for the 4-wide SAH walk
+  // (up to three pushes per level)
+  if (S.max_depth > (kind == BVH_SAH ? 42 : 60)) { err = "BVH too deep"; return RT_ERR_UNSUPPORTED; }
   // resolve light slots
   {
     std::vector<int> obj_to_slot(n, -1);
