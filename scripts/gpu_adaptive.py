@@ -1,5 +1,5 @@
 """Adaptive-sampling / render-mode renders (the reference's defaults: aTolerance 0.05, aBatch 10): image hash,
-stats and time, to compare kernel variants (RT_B200_OLD_PIXELS=1 selects the tile-synchronous kernel).
+stats and time, to compare kernel variants.
 usage: gpu_adaptive.py [width] [spp] [workloads...]"""
 import hashlib, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

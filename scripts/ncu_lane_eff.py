@@ -1,3 +1,4 @@
+"""Share of samples and warp instructions per lanes-active bucket of an .ncu-rep (source page)."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
