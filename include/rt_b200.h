@@ -71,7 +71,7 @@ enum { RT_MODE_DEFAULT = 0, RT_MODE_BOUNCES = 1, RT_MODE_SAMPLES = 2 };
  * on equal t).  SAH = binned-SAH tree with near-first ordering: same nearest hits except
  * for those quirks.  LIST = no hierarchy, every object tested (<= 128 objects; what the
  * reference's BVH degenerates to on Cornell).  AUTO picks REFERENCE when the scene has a
- * negative-radius sphere, LIST for <= 10 objects (<= 64 in a room: five or more quads/planes;
+ * negative-radius sphere, LIST for <= 16 objects (<= 64 in a room: five or more quads/planes;
  * both crossovers measured), SAH otherwise. */
 enum { RT_BVH_AUTO = 0, RT_BVH_REFERENCE = 1, RT_BVH_SAH = 2, RT_BVH_LIST = 3 };
 

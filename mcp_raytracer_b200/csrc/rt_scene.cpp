@@ -659,15 +659,15 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   if (kind == RT_BVH_AUTO) {
     if (any_negative) kind = BVH_REFERENCE;      // inverted boxes are only meaningful in the reference topology
     // Measured with the 4-wide while-while tree walk.  Open scene (scripts/gpu_list_vs_sah.py, spheres over a
-    // ground; LIST / SAH ms): 9 objects 2.6 / 3.1, 13: 3.2 / 3.1, 17: 3.9 / 3.5, 25: 5.1 / 3.8, 33: 6.4 / 4.3.
+    // ground; LIST / SAH ms): 13 objects 2.8 / 2.9, 17: 3.35 / 3.40, 25: 4.3 / 3.6, 33: 5.4 / 4.1, 49: 7.5 / 5.0.
     // Room (the 55-object layered/mixed box: walls everywhere, every ray hits, and only the LIST kernel has the
-    // axis-aligned quad test): LIST 457 / 483 ms vs SAH 535 / 638 ms (fixed spp / adaptive); SAH wins there only
-    // with the sorted integrator at fixed spp (404 vs 430 ms).  Cornell (8 objects) is the LIST kernel's case.
+    // axis-aligned quad test): LIST 370 / 416 ms vs SAH 418 / 591 ms (fixed spp with the sorted integrator /
+    // adaptive).  Cornell (8 objects) is the LIST kernel's case.
     else {
       uint32_t n_planar = 0;
       for (uint32_t i = 0; i < n; ++i) n_planar += P[i].type != OBJ_SPHERE;
       const bool room = n_planar >= 5;
-      kind = n <= (room ? 64u : 10u) ? BVH_LIST : BVH_SAH;
+      kind = n <= (room ? 64u : 16u) ? BVH_LIST : BVH_SAH;
     }
   }
   if (kind != BVH_REFERENCE && kind != BVH_SAH && kind != BVH_LIST) { err = "invalid bvh kind"; return RT_ERR_INVALID_ARGUMENT; }
