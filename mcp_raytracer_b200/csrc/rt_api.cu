@@ -298,6 +298,8 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   d.bvh_kind = c->hs.bvh_kind;
   d.planar_any = c->hs.planar_any;
   for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs.list_n[k];
+  d.sph_cmax = c->hs.sph_cmax;
+  d.sph_r2max = c->hs.sph_r2max;
   d.seed_lo = (uint32_t)opts->seed;
   d.seed_hi = (uint32_t)(opts->seed >> 32);
   if (dev_alloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||

@@ -722,6 +722,11 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
         if (group_of(pi) == g) { fl.push_slot(pi); S.list_n[g]++; }
     }
     S.n_unbounded = (int)n; // every slot is "always tested"
+    for (uint32_t i = 0; i < n; ++i) // constants of the sphere loop's cheap miss test (rt_device.cuh)
+      if (P[i].type == OBJ_SPHERE) {
+        for (int a = 0; a < 3; ++a) S.sph_cmax = std::max(S.sph_cmax, std::fabs(P[i].q[a]));
+        S.sph_r2max = std::max(S.sph_r2max, (float)(P[i].r * P[i].r));
+      }
   } else if (kind == BVH_REFERENCE) {
     // node 0 = super-root: the reference tests the root's own box first (bvh.ts:130)
     S.nodes.emplace_back();

@@ -18,6 +18,7 @@ struct HostScene {
   int n_unbounded = 0;
   int planar_any = 0;
   int list_n[6] = {0, 0, 0, 0, 0, 0}; // LIST: slots per kind (spheres, aa-quads x/y/z, quads, planes)
+  float sph_cmax = 0, sph_r2max = 0;  // LIST: max |centre component| and max r^2 over the spheres
   int max_depth = 0; // deepest leaf below node 0
   std::vector<Node> nodes;
   std::vector<F4> p0, p1, p2, p3;

@@ -109,6 +109,7 @@ struct DevScene {
   int bvh_kind;
   int planar_any; // scene has planes/quads
   int list_n[6];  // LIST: slots per kind, in slot order: spheres, axis-aligned quads x/y/z, general quads, planes
+  float sph_cmax, sph_r2max; // LIST: max |centre component| and max r^2 over the spheres
   uint32_t seed_lo, seed_hi;
 };
 
