@@ -69,6 +69,65 @@ def test_primary_hits_match_oracle(gpu, name, bvh):
     assert np.all(np.isinf(t[~hit]))
 
 
+def _random_scene(seed, n):
+    """Seeded mix of spheres (tiny ... scene-sized), axis-aligned and rotated quads and an occasional infinite
+    plane: exercises every AUTO choice (LIST / room rule / SAH), the always-tested prefix and the 4-wide tree."""
+    rng = np.random.default_rng(seed)
+    objs = []
+    mats = [{"type": "lambert", "color": [0.7, 0.6, 0.5]}, {"type": "metal", "color": [0.8, 0.8, 0.8], "fuzz": 0.1},
+            {"type": "glass", "ior": 1.5}]
+    for k in range(n):
+        m = mats[int(rng.integers(0, 3))]
+        kind = rng.random()
+        c = (rng.random(3) * 8 - 4).tolist()
+        if kind < 0.6:
+            objs.append({"type": "sphere", "pos": c, "r": float(10 ** rng.uniform(-1.5, 0.2)), "material": m})
+        elif kind < 0.8:  # axis-aligned quad
+            ax = int(rng.integers(0, 3))
+            u, v = [0.0] * 3, [0.0] * 3
+            u[(ax + 1) % 3] = float(rng.uniform(0.3, 3))
+            v[(ax + 2) % 3] = float(rng.uniform(0.3, 3)) * (1 if rng.random() < 0.5 else -1)
+            objs.append({"type": "quad", "pos": c, "u": u, "v": v, "material": m})
+        elif kind < 0.97:  # rotated quad
+            objs.append({"type": "quad", "pos": c, "u": (rng.random(3) * 2 - 1).tolist(), "v": (rng.random(3) * 2 - 1).tolist(), "material": m})
+        else:
+            objs.append({"type": "plane", "pos": [0, -4.5, 0], "u": [1, 0, 0.1 * float(rng.random())], "v": [0, 0.05 * float(rng.random()), 1], "material": m})
+    if seed % 2 == 0:  # a ground sphere as large as the scene
+        objs.append({"type": "sphere", "pos": [0, -1004, 0], "r": 1000, "material": mats[0]})
+    return {"type": "custom", "camera": {"vfov": 60, "from": [0.3, 1.1, 9], "at": [0, 0, 0]}, "objects": objs}
+
+
+@pytest.mark.parametrize("seed,n", [(1, 6), (2, 14), (3, 30), (4, 30), (5, 90), (6, 400), (7, 3000)])
+@pytest.mark.parametrize("bvh", ["auto", "sah"])
+def test_primary_hits_random_scenes(gpu, seed, n, bvh):
+    sd = _random_scene(seed, n)
+    opts = {"width": 256, "samples": 1, "bvh": bvh}
+    with createCameraFromSceneData(sd, opts) as cam:
+        ids, t, nrm, ff = cam.tracePrimary()
+    oids, ot, onrm, off = ob.OracleCamera(sd, opts).trace_primary()
+    assert np.array_equal(ids, oids), f"{int((ids != oids).sum())} primary-hit ids differ (seed {seed}, {n} objects, bvh {bvh})"
+    hit = oids >= 0
+    assert np.all(np.abs(t[hit] - ot[hit]) <= 1e-4 * np.abs(ot[hit]))
+    assert np.all(np.abs(nrm[hit] - onrm[hit]) <= 2e-4)
+    assert np.array_equal(ff[hit], off[hit])
+
+
+@pytest.mark.parametrize("seed,n", [(2, 14), (3, 30), (6, 400), (7, 3000)])
+def test_integrators_agree_on_random_scenes(gpu, seed, n):
+    """All integrator layouts and both tree choices walk the same paths: bit-identical images within a build."""
+    sd = _random_scene(seed, n)
+    opts = {"width": 120, "samples": 12, "aTolerance": 0, "seed": seed}
+    ref = gpu_render(sd, {**opts, "integrator": "megakernel"})
+    for integ in ("sorted", "wavefront"):
+        other = gpu_render(sd, {**opts, "integrator": integ})
+        assert np.array_equal(ref["linear"], other["linear"]), integ
+        assert ref["stats"].rays == other["stats"].rays
+    adaptive = {**opts, "samples": 40, "aTolerance": 0.05}
+    a = gpu_render(sd, adaptive, want_moments=True)
+    b = gpu_render(sd, {**adaptive, "partIndex": 0, "partCount": 1}, region={"x": 0, "y": 0, "width": 120, "height": 40})
+    assert np.array_equal(a["rgb8"][:40], b["rgb8"][:40])
+
+
 def test_primary_hits_full_size_C1(gpu):
     """BASELINE.json configs[0] at its full size (400x225)."""
     sd = SCENES["C1-spheres"]()
