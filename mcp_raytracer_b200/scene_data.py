@@ -192,6 +192,8 @@ class FlatScene:
         rs: List[float] = []
         lights: List[int] = []
         zero3 = (0.0, 0.0, 0.0)
+        # (the per-object part of this loop is ~60 ms per 100 k objects; the rest of the ~0.2 s is the material
+        #  table, one `_material` call per distinct material — comprehensions instead of this loop gained nothing)
         for ob in objs:
             # scenes.ts:113 creates the material first, then switches on the object type
             mats.append(self._material(ob.get("material"), materials))
