@@ -1405,9 +1405,8 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
     case BVH_SAH:
       // Whole-query while-while walk (k_render_pool) vs traversal bursts interleaved with shading (k_render_trav),
       // rain scene at 1 k ... 100 k spheres with the 4-wide tree (scripts/gpu_trav_threshold.py; n_nodes counts
-      // 64-byte slots): 4.9 / 7.8 ms at 0.6 k, 8.0 / 11.1 at 1.8 k, 12.6 / 15.0 at 4.9 k, 19.1 / 19.5 at 11.8 k,
-      // 27.3 / ~24 at 28.6 k, 37.8 / 30.2 at 63.7 k: regenerating paths mid-traversal pays once lanes diverge by
-      // many node visits.
+      // 64-byte slots; final tree layout): 11.7 / 15.2 ms at 8 k slots (8 000 spheres), 19.2 / 18.1 at 20 k,
+      // 27.5 / 22.9 at 48.5 k: regenerating paths mid-traversal pays once lanes diverge by many node visits.
       if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
         static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
