@@ -90,13 +90,13 @@ RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
   return L;
 }
 
-template <int KIND>
+template <int KIND, bool LEAF_LOOP = true> // LEAF_LOOP: see leaves_intersect (rt_device.cuh)
 RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
   RayPre pre = precompute(r, true); // LIST uses idir too (axis-aligned quads); unused parts are dead code
   t = CUDART_INF_F;
   slot = -1;
   if (KIND == BVH_LIST) trace_list(S, L, r, pre, t, slot);
-  else if (KIND == BVH_SAH) trace_sah(S, r, pre, t, slot);
+  else if (KIND == BVH_SAH) trace_sah<LEAF_LOOP>(S, r, pre, t, slot);
   else trace_ref(S, r, pre, t, slot);
   return slot >= 0;
 }
@@ -194,14 +194,14 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
 }
 
 // One whole rayColor call on the path's current ray.
-template <int KIND>
+template <int KIND, bool LEAF_LOOP = true>
 RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
                       unsigned& rays) {
   if (path_pre(S.cam, ps, g)) return true;
   float t;
   int slot;
   ++rays;
-  closest_hit<KIND>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
+  closest_hit<KIND, LEAF_LOOP>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
   return path_post<KIND>(S, &sm, mw, ps, g, t, slot);
 }
 
@@ -1082,7 +1082,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         ps.ray = camera_ray(cam, i, j, g, true);
         need_path = false;
       }
-      if (path_step<KIND>(S, L, sm, mw, ps, g, t_rays)) { // pixel.add(rayColor, bounces, useAdaptiveSampling)
+      if (path_step<KIND, false>(S, L, sm, mw, ps, g, t_rays)) { // pixel.add(rayColor, bounces, useAdaptiveSampling)
         color = color + ps.radiance;
         ++samples;
         bounces_sum += (unsigned)ps.bounces;
