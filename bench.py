@@ -196,6 +196,11 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # `python bench.py --gpus N` without a launcher: become the one-process-per-GPU job the contract describes
+        port = 29500 + os.getpid() % 2000
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                                   "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
     # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there)
     # are sent to stderr for the duration of the run.
     sys.stdout.flush()
