@@ -231,6 +231,24 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
  * more than the scene build).  This returns them to the driver; result = bytes released. */
 uint64_t rt_trim_device_cache(void);
 
+/* Host-only diagnostic (no GPU needed): runs the scene compiler of rt_camera_create — validation of
+ * createSceneObject/createMaterial (src/scenes/scenes.ts:109-199), acceleration-structure choice and build —
+ * and checks the result: every object in exactly one slot, every leaf primitive inside its child box, every
+ * child box inside its parent's, stack depth.  `errors` = number of violated invariants (0 = sound). */
+typedef struct rt_scene_report {
+  int32_t bvh_kind;      /* RT_BVH_* actually chosen */
+  int32_t n_slots;       /* primitive slots = objects */
+  int32_t n_prefix;      /* always-tested slots (all of them for RT_BVH_LIST) */
+  int32_t n_node_slots;  /* 64-byte node slots (a 4-wide SAH node takes two) */
+  int32_t n_leaves;
+  int32_t max_leaf_size;
+  int32_t max_depth;
+  int32_t n_lights;
+  int32_t errors;
+  int32_t reserved[3];
+} rt_scene_report;
+rt_status rt_scene_validate(const rt_scene_desc* scene, const rt_render_opts* opts, rt_scene_report* report);
+
 #ifdef __cplusplus
 }
 #endif

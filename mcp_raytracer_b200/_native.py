@@ -21,7 +21,7 @@ EXPORTS = [
     "rt_camera_create", "rt_camera_destroy", "rt_camera_get_info", "rt_camera_set_stream",
     "rt_camera_render_region", "rt_camera_render", "rt_camera_render_region_device",
     "rt_camera_render_moments", "rt_camera_trace_primary", "rt_last_error", "rt_device_count",
-    "rt_abi_version", "rt_measure_fp32_peak", "rt_trim_device_cache",
+    "rt_abi_version", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
 ]
 
 STATUS_NAMES = {
@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
     L.rt_camera_trace_primary.argtypes = [vp, C.POINTER(rt_region), vp, vp, vp, vp]
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.rt_trim_device_cache.restype = C.c_uint64
+    L.rt_scene_validate.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), vp]
     _lib = L
     return L
 

@@ -218,6 +218,23 @@ def measureFp32Peak(device: int = -1):
     return t.value, mhz.value
 
 
+class _SceneReport(C.Structure):  # rt_scene_report (include/rt_b200.h)
+    _fields_ = [(n, C.c_int32) for n in ("bvh_kind", "n_slots", "n_prefix", "n_node_slots", "n_leaves", "max_leaf_size",
+                                         "max_depth", "n_lights", "errors")] + [("reserved", C.c_int32 * 3)]
+
+
+def validateScene(sceneData: Dict[str, Any], renderOptions: Optional[Dict[str, Any]] = None) -> Dict[str, int]:
+    """Host-only (no GPU): run the scene compiler of `createCameraFromSceneData` and check the structure the
+    kernels walk (rt_scene_validate).  Raises the reference's errors for a bad scene; `errors` must be 0."""
+    flat = FlatScene(sceneData)
+    opts = render_opts_struct(merge_render_options(flat.render, renderOptions))
+    rep = _SceneReport()
+    st = _native.lib().rt_scene_validate(C.byref(flat.desc), C.byref(opts), C.byref(rep))
+    if st != 0:
+        raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
+    return {n: int(getattr(rep, n)) for n, _ in _SceneReport._fields_ if n != "reserved"}
+
+
 def trimDeviceCache() -> int:
     """Return the device buffers kept from destroyed cameras to the driver (rt_trim_device_cache); bytes released."""
     return int(_native.lib().rt_trim_device_cache())

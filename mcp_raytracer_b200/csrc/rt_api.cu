@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -237,6 +238,116 @@ uint64_t rt_trim_device_cache(void) {
   DevCache& C = dev_cache();
   std::lock_guard<std::mutex> lk(C.mu);
   return (uint64_t)dev_trim_locked(C);
+}
+
+// Host-only: compile the scene like rt_camera_create and check the structure the kernels will walk.
+rt_status rt_scene_validate(const rt_scene_desc* scene, const rt_render_opts* opts, rt_scene_report* rep) {
+  if (!scene || !opts || !rep) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  HostScene hs;
+  std::string err;
+  rt_status st = compile_scene(scene, opts, hs, err);
+  if (st != RT_OK) return fail(st, err);
+  std::memset(rep, 0, sizeof(*rep));
+  const int n = (int)hs.p0.size();
+  rep->bvh_kind = hs.bvh_kind;
+  rep->n_slots = n;
+  rep->n_prefix = hs.n_unbounded;
+  rep->n_node_slots = (int)hs.nodes.size();
+  rep->max_depth = hs.max_depth;
+  rep->n_lights = (int)hs.lights.size();
+  int errors = 0;
+  // every object sits in exactly one slot
+  std::vector<int> seen_obj(hs.n_objects, 0), seen_slot(n, 0);
+  if (n != hs.n_objects) ++errors;
+  for (int s = 0; s < n; ++s) {
+    const int obj = hs.slot_info[s].y & 0x3fffffff;
+    if (obj < 0 || obj >= hs.n_objects || seen_obj[obj]++) ++errors;
+  }
+  for (int s = 0; s < hs.n_unbounded && s < n; ++s) seen_slot[s]++;
+  struct B { float mn[3], mx[3]; };
+  auto inside = [](const B& in, const B& out) { // with the slack of the FP32 roundings that made the boxes
+    for (int a = 0; a < 3; ++a) {
+      const float tol = 1e-5f * std::max(1.f, std::max(std::fabs(in.mn[a]), std::fabs(in.mx[a])));
+      if (in.mn[a] < out.mn[a] - tol || in.mx[a] > out.mx[a] + tol) return false;
+    }
+    return true;
+  };
+  auto inverted = [](const B& b) { return b.mn[0] > b.mx[0] || b.mn[1] > b.mx[1] || b.mn[2] > b.mx[2]; };
+  auto prim_box = [&](int s, B& b) { // false: unbounded (plane)
+    const ExactPrim& e = hs.exact[s];
+    if (e.type == OBJ_SPHERE) {
+      const float r = std::fabs((float)e.r);
+      for (int a = 0; a < 3; ++a) { b.mn[a] = e.q[a] - r; b.mx[a] = e.q[a] + r; }
+      return true;
+    }
+    if (e.type == OBJ_QUAD) {
+      for (int a = 0; a < 3; ++a) {
+        const float c[4] = {e.q[a], e.q[a] + e.u[a], e.q[a] + e.v[a], e.q[a] + e.u[a] + e.v[a]};
+        b.mn[a] = std::min(std::min(c[0], c[1]), std::min(c[2], c[3]));
+        b.mx[a] = std::max(std::max(c[0], c[1]), std::max(c[2], c[3]));
+      }
+      return true;
+    }
+    return false;
+  };
+  auto check_leaf = [&](int ref, const B& box) {
+    const int v = ~ref, first = v >> 6, count = ((v >> 4) & 3) + 1, mask = v & 15;
+    ++rep->n_leaves;
+    rep->max_leaf_size = std::max(rep->max_leaf_size, count);
+    for (int k = 0; k < count; ++k) {
+      const int s = first + k;
+      if (s < 0 || s >= n) { ++errors; continue; }
+      seen_slot[s]++;
+      if (((mask >> k) & 1) != (hs.exact[s].type != OBJ_SPHERE)) ++errors; // planar mask matches the slot's type
+      B pb;
+      if (prim_box(s, pb) && !inverted(box) && !(hs.exact[s].r < 0) && !inside(pb, box)) ++errors;
+    }
+  };
+  if (hs.bvh_kind == BVH_SAH && !hs.nodes.empty()) {
+    const WideNode* W = reinterpret_cast<const WideNode*>(hs.nodes.data());
+    const int nw = (int)hs.nodes.size() / 2;
+    std::vector<int> visited(nw, 0);
+    std::vector<std::pair<int, B>> todo; // (wide node, the box its parent holds for it)
+    B all;
+    for (int a = 0; a < 3; ++a) { all.mn[a] = -INFINITY; all.mx[a] = INFINITY; }
+    todo.push_back({0, all});
+    while (!todo.empty()) {
+      const int idx = todo.back().first;
+      const B pbox = todo.back().second;
+      todo.pop_back();
+      if (idx < 0 || idx >= nw || visited[idx]++) { ++errors; continue; }
+      for (int k = 0; k < 4; ++k) {
+        const int ref = W[idx].ref[k];
+        if (ref == kEmptyRef) continue;
+        B cb;
+        for (int a = 0; a < 3; ++a) { cb.mn[a] = W[idx].box[k][a]; cb.mx[a] = W[idx].box[k][3 + a]; }
+        if (!inside(cb, pbox)) ++errors;
+        if (ref < 0) check_leaf(ref, cb);
+        else todo.push_back({ref, cb});
+      }
+    }
+    for (int v : visited) if (v != 1) ++errors;
+  } else if (hs.bvh_kind == BVH_REFERENCE && !hs.nodes.empty()) {
+    std::vector<int> visited(hs.nodes.size(), 0);
+    std::vector<int> todo{0};
+    while (!todo.empty()) {
+      const int idx = todo.back();
+      todo.pop_back();
+      if (idx < 0 || idx >= (int)hs.nodes.size() || visited[idx]++) { ++errors; continue; }
+      const Node& nd = hs.nodes[idx];
+      const int refs[2] = {nd.left, nd.right};
+      for (int k = 0; k < 2; ++k) {
+        if (refs[k] == kEmptyRef) continue;
+        B cb;
+        for (int a = 0; a < 3; ++a) { cb.mn[a] = k ? nd.rmin[a] : nd.lmin[a]; cb.mx[a] = k ? nd.rmax[a] : nd.lmax[a]; }
+        if (refs[k] < 0) check_leaf(refs[k], cb);
+        else todo.push_back(refs[k]);
+      }
+    }
+  }
+  for (int s = 0; s < n; ++s) if (seen_slot[s] != 1) ++errors;
+  rep->errors = errors;
+  return RT_OK;
 }
 int32_t rt_device_count(void) {
   int n = 0;

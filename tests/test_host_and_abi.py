@@ -78,6 +78,79 @@ def test_scene_errors_are_reported_before_device_checks():
     assert b"Unknown object type" in L.rt_last_error()
 
 
+def _mixed_scene(seed, n):
+    """Seeded mix of spheres (tiny ... scene-sized), axis-aligned / rotated quads and an occasional infinite plane."""
+    rng = np.random.default_rng(seed)
+    m = {"type": "lambert", "color": [0.7, 0.6, 0.5]}
+    objs = []
+    for _ in range(n):
+        kind = rng.random()
+        c = (rng.random(3) * 8 - 4).tolist()
+        if kind < 0.6:
+            objs.append({"type": "sphere", "pos": c, "r": float(10 ** rng.uniform(-1.5, 0.2)), "material": m})
+        elif kind < 0.8:
+            ax = int(rng.integers(0, 3))
+            u, v = [0.0] * 3, [0.0] * 3
+            u[(ax + 1) % 3] = float(rng.uniform(0.3, 3))
+            v[(ax + 2) % 3] = -float(rng.uniform(0.3, 3))
+            objs.append({"type": "quad", "pos": c, "u": u, "v": v, "material": m})
+        elif kind < 0.97:
+            objs.append({"type": "quad", "pos": c, "u": (rng.random(3) * 2 - 1).tolist(), "v": (rng.random(3) * 2 - 1).tolist(), "material": m})
+        else:
+            objs.append({"type": "plane", "pos": [0, -4.5, 0], "u": [1, 0, 0.05], "v": [0, 0.02, 1], "material": m})
+    if seed % 2 == 0:
+        objs.append({"type": "sphere", "pos": [0, -1004, 0], "r": 1000, "material": m})
+    return {"type": "custom", "camera": {"vfov": 60, "from": [0.3, 1.1, 9], "at": [0, 0, 0]}, "objects": objs}
+
+
+def test_scene_compiler_structures_are_sound():
+    """rt_scene_validate (host only): every object in exactly one slot, every leaf primitive inside its child box,
+    every child box inside its parent's, for every acceleration structure the kernels walk — the 4-wide SAH tree
+    with its always-tested prefix, the reference's own topology, the LIST."""
+    from mcp_raytracer_b200 import (generateCornellSceneData, generateDefaultSceneData, generateLayeredMixedSceneData,
+                                    generateRainSceneData, generateSpheresSceneData, generateWeekendFinalSceneData, validateScene)
+
+    scenes = {
+        "cornell": generateCornellSceneData(), "layered": generateLayeredMixedSceneData(), "default": generateDefaultSceneData(),
+        "spheres": generateSpheresSceneData({"count": 100, "seed": 12345}), "weekend": generateWeekendFinalSceneData(),
+        "rain": generateRainSceneData({"count": 50000, "seed": 1, "sphereRadius": 0.01}),
+    }
+    for seed, n in ((1, 5), (2, 14), (3, 40), (4, 300), (6, 5000)):
+        scenes[f"mixed{seed}"] = _mixed_scene(seed, n)
+    for name, sd in scenes.items():
+        n_obj = len(sd["objects"])
+        for bvh in ("auto", "sah", "reference") + (("list",) if n_obj <= 128 else ()):
+            rep = validateScene(sd, {"bvh": bvh})
+            assert rep["errors"] == 0, (name, bvh, rep)
+            assert rep["n_slots"] == n_obj
+            if rep["bvh_kind"] == 2:
+                assert rep["max_depth"] <= 42 and rep["max_leaf_size"] <= 4
+                assert rep["n_leaves"] + rep["n_prefix"] <= n_obj
+            if rep["bvh_kind"] == 3:
+                assert rep["n_prefix"] == n_obj and rep["n_node_slots"] == 0
+    # the AUTO rules (include/rt_b200.h): room -> LIST, open scene beyond 16 objects -> SAH, negative radius -> REFERENCE
+    assert validateScene(scenes["cornell"])["bvh_kind"] == 3
+    assert validateScene(scenes["layered"])["bvh_kind"] == 3
+    assert validateScene(scenes["spheres"])["bvh_kind"] == 2
+    assert validateScene(scenes["default"])["bvh_kind"] == 1
+    weekend = validateScene(scenes["weekend"])
+    assert weekend["bvh_kind"] == 2 and weekend["n_prefix"] == 1  # the r = 1000 ground sphere is tested outside the tree
+    assert validateScene(scenes["rain"])["n_prefix"] == 0        # big scenes keep everything in the tree
+
+
+def test_scene_validate_raises_the_reference_errors():
+    from mcp_raytracer_b200 import RaytracerError, generateCornellSceneData, validateScene
+
+    bad = generateCornellSceneData()
+    bad["objects"][2]["material"] = "no-such-material"
+    with pytest.raises(RaytracerError, match="Material not found"):
+        validateScene(bad)
+    bad = generateCornellSceneData()
+    bad["objects"][0]["type"] = "torus"
+    with pytest.raises(RaytracerError, match="Unknown object type"):
+        validateScene(bad)
+
+
 def test_product_package_never_touches_the_oracle():
     """The oracle is the checker: nothing under the product package may import, link or open it."""
     pkg = os.path.join(ROOT, "mcp_raytracer_b200")
