@@ -196,6 +196,24 @@ dist.destroy_process_group()
 '''
 
 
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference, no GPU involved): exactly one JSON line on stdout
+    with the keys the driver reads; under a 2-process launch only rank 0 prints."""
+    import json
+
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-seconds", "1"]
+    for extra in ([], ["--gpus", "2"]):
+        out = subprocess.run(cmd + extra, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=300, check=True).stdout.decode()
+        lines = [l for l in out.splitlines() if l.strip()]
+        assert len(lines) == 1, out
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == "Mpaths/s" and d["unit"] == "Mpaths/s" and d["higher_is_better"] is True
+        assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == (2 if extra else 1)
+        assert "cornell" in d["config"]["workload"] and "model" not in d["config"]
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+        assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
 def test_gloo_world_size_2_gather_and_stats(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
