@@ -181,6 +181,19 @@ static rt_status upload(rt_camera* c, const std::vector<T>& v, const T** out) {
   return RT_OK;
 }
 
+// Path pool and queues of the wavefront integrator; also the clean-up of a pool whose allocation failed half way
+// (every pointer is null until allocated: rt_camera value-initialises WfHost).
+static void wf_release(rt_camera* c) {
+  WfBuffers& W = c->wf.W;
+  dev_free(W.ray_o); dev_free(W.ray_d); dev_free(W.tp); dev_free(W.rad); dev_free(W.pix);
+  for (int k = 0; k < WF_TAGS; ++k) dev_free(W.q_shade[k]);
+  dev_free(c->wf.q_extend[0]); dev_free(c->wf.q_extend[1]); dev_free(c->wf.q_free[0]); dev_free(c->wf.q_free[1]);
+  dev_free(W.counters); dev_free(c->wf.owned_blocks);
+  if (c->wf.h_counters) cudaFreeHost(c->wf.h_counters);
+  std::memset(&c->wf, 0, sizeof(c->wf));
+  c->wf_ready = false;
+}
+
 static void free_camera(rt_camera* c) {
   if (!c) return;
   DeviceGuard g(c->device);
@@ -188,14 +201,7 @@ static void free_camera(rt_camera* c) {
   for (void* p : c->allocs) dev_free(p);
   dev_free(c->d_rgb8); dev_free(c->d_linear); dev_free(c->d_moments); dev_free(c->d_ids);
   dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch);
-  if (c->wf_ready) {
-    WfBuffers& W = c->wf.W;
-    dev_free(W.ray_o); dev_free(W.ray_d); dev_free(W.tp); dev_free(W.rad); dev_free(W.pix);
-    for (int k = 0; k < WF_TAGS; ++k) dev_free(W.q_shade[k]);
-    dev_free(c->wf.q_extend[0]); dev_free(c->wf.q_extend[1]); dev_free(c->wf.q_free[0]); dev_free(c->wf.q_free[1]);
-    dev_free(W.counters); dev_free(c->wf.owned_blocks);
-    cudaFreeHost(c->wf.h_counters);
-  }
+  wf_release(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   delete c;
@@ -457,6 +463,11 @@ rt_status rt_camera_get_info(const rt_camera* c, rt_camera_info* o) {
 
 rt_status rt_camera_set_stream(rt_camera* c, void* s) {
   if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  if (c->stream != (cudaStream_t)s) {
+    // work already enqueued on the old stream uses this camera's buffers; destroy/realloc only wait for the current one
+    DeviceGuard g(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+  }
   c->stream = (cudaStream_t)s;
   return RT_OK;
 }
@@ -481,18 +492,28 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
     const int n = slots_env > 0 ? slots_env : (1 << 22); // 4 Mi paths in flight, 80 B each
     WfBuffers& W = H.W;
     W.n_slots = n;
-    CU(dev_alloc(&W.ray_o, (size_t)n * sizeof(F4)));
-    CU(dev_alloc(&W.ray_d, (size_t)n * sizeof(F4)));
-    CU(dev_alloc(&W.tp, (size_t)n * sizeof(F4)));
-    CU(dev_alloc(&W.rad, (size_t)n * sizeof(F4)));
-    CU(dev_alloc(&W.pix, (size_t)n * sizeof(U2)));
-    for (int k = 0; k < WF_TAGS; ++k) CU(dev_alloc(&W.q_shade[k], (size_t)n * sizeof(int)));
-    for (int k = 0; k < 2; ++k) {
-      CU(dev_alloc(&H.q_extend[k], (size_t)n * sizeof(int)));
-      CU(dev_alloc(&H.q_free[k], (size_t)n * sizeof(int)));
+    auto alloc_pool = [&]() -> cudaError_t {
+      cudaError_t e;
+      if ((e = dev_alloc(&W.ray_o, (size_t)n * sizeof(F4))) != cudaSuccess) return e;
+      if ((e = dev_alloc(&W.ray_d, (size_t)n * sizeof(F4))) != cudaSuccess) return e;
+      if ((e = dev_alloc(&W.tp, (size_t)n * sizeof(F4))) != cudaSuccess) return e;
+      if ((e = dev_alloc(&W.rad, (size_t)n * sizeof(F4))) != cudaSuccess) return e;
+      if ((e = dev_alloc(&W.pix, (size_t)n * sizeof(U2))) != cudaSuccess) return e;
+      for (int k = 0; k < WF_TAGS; ++k)
+        if ((e = dev_alloc(&W.q_shade[k], (size_t)n * sizeof(int))) != cudaSuccess) return e;
+      for (int k = 0; k < 2; ++k) {
+        if ((e = dev_alloc(&H.q_extend[k], (size_t)n * sizeof(int))) != cudaSuccess) return e;
+        if ((e = dev_alloc(&H.q_free[k], (size_t)n * sizeof(int))) != cudaSuccess) return e;
+      }
+      if ((e = dev_alloc(&W.counters, WFC_COUNT * sizeof(int))) != cudaSuccess) return e;
+      return cudaMallocHost(&H.h_counters, WFC_COUNT * sizeof(int));
+    };
+    const cudaError_t pe = alloc_pool();
+    if (pe != cudaSuccess) { // nothing half-built stays behind: the next render may try again
+      cudaGetLastError();
+      wf_release(c);
+      return fail(RT_ERR_CUDA, std::string("wavefront path pool: ") + cudaGetErrorString(pe));
     }
-    CU(dev_alloc(&W.counters, WFC_COUNT * sizeof(int)));
-    CU(cudaMallocHost(&H.h_counters, WFC_COUNT * sizeof(int)));
     c->wf_ready = true;
   }
   if ((int)owned.size() > H.owned_capacity) {
@@ -716,24 +737,25 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
   const int blocks = sms * 16, iters = 2048;
   float* d = nullptr;
   CU(dev_alloc(&d, (size_t)blocks * 256 * sizeof(float)));
-  cudaEvent_t a, b;
-  CU(cudaEventCreate(&a));
-  CU(cudaEventCreate(&b));
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaError_t e = cudaEventCreate(&a);
+  if (e == cudaSuccess) e = cudaEventCreate(&b);
   double best = 0;
-  for (int rep = 0; rep < 5; ++rep) {
-    CU(cudaEventRecord(a, 0));
-    CU(launch_fp32_peak(d, blocks, iters, 0));
-    CU(cudaEventRecord(b, 0));
-    CU(cudaEventSynchronize(b));
+  for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, a, b));
+    if ((e = cudaEventRecord(a, 0)) != cudaSuccess) break;
+    if ((e = launch_fp32_peak(d, blocks, iters, 0)) != cudaSuccess) break;
+    if ((e = cudaEventRecord(b, 0)) != cudaSuccess) break;
+    if ((e = cudaEventSynchronize(b)) != cudaSuccess) break;
+    if ((e = cudaEventElapsedTime(&ms, a, b)) != cudaSuccess) break;
     double flops = (double)blocks * 256.0 * iters * 16.0 * 8.0 * 2.0;
     double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0 && tf > best) best = tf;
   }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
+  if (a) cudaEventDestroy(a);
+  if (b) cudaEventDestroy(b);
   dev_free(d);
+  if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("FP32 peak measurement: ") + cudaGetErrorString(e));
   *tflops = best;
   if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
   return RT_OK;
