@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--bvh", default="auto")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=None,
+                    help="threads of the CPU port (default: host cores - 1 like the reference; 1 = the scalar figure SURVEY 8d asks for)")
     args = ap.parse_args()
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
         # `python bench.py --gpus N` without a launcher: become the one-process-per-GPU job the contract describes
@@ -222,6 +224,8 @@ def main():
         ropts["width"] = args.width; overridden = True
     ropts["bvh"] = args.bvh
     cpu_threads = max(1, (os.cpu_count() or 2) - 1)  # os.cpus().length - 1, src/raytracer.ts:61
+    if args.cpu_threads:
+        cpu_threads = max(1, args.cpu_threads)
 
     # ---------------------------------------------------------------- reference arm (CPU port)
     if args.impl == "reference":
