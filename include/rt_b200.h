@@ -38,7 +38,7 @@ extern "C" {
 
 typedef enum rt_status {
   RT_OK = 0,
-  RT_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad size, bad region */
+  RT_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad size, bad region; object geometry that is not finite in FP32 */
   RT_ERR_UNKNOWN_OBJECT_TYPE = 2, /* reference: `Unknown object type` src/scenes/scenes.ts:137 */
   RT_ERR_UNKNOWN_MATERIAL_TYPE = 3, /* reference: `Unknown material type` src/scenes/scenes.ts:178 */
   RT_ERR_MATERIAL_NOT_FOUND = 4, /* reference: `Material not found` src/scenes/scenes.ts:154,191 */

@@ -577,6 +577,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   };
   // ---- materials (createMaterial, scenes.ts:144-199) ----
   const uint32_t nm = sd->n_materials;
+  if (nm && (!sd->mat_type || !sd->mat_color || !sd->mat_param)) { err = "material arrays missing"; return RT_ERR_INVALID_ARGUMENT; }
   S.matA.resize(nm); S.matB.resize(nm); S.matE.resize(nm);
   for (uint32_t i = 0; i < nm; ++i) {
     int ty = sd->mat_type[i];
@@ -619,6 +620,10 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   std::vector<Prim> P(n);
   bool any_negative = false, any_unbounded = false;
   S.planar_any = 0;
+  // Geometry that is not finite in FP32 (the reference's Float32Array storage) renders NaN in the reference and
+  // has no meaningful box for any tree: refuse it here instead of building on it.
+  auto finite3 = [](const H3& a) { return std::isfinite(a[0]) && std::isfinite(a[1]) && std::isfinite(a[2]); };
+  auto not_finite = [&](uint32_t i) { err = "object " + std::to_string(i) + " has non-finite geometry"; return RT_ERR_INVALID_ARGUMENT; };
   for (uint32_t i = 0; i < n; ++i) {
     Prim& p = P[i];
     int mi = sd->obj_material[i];
@@ -627,14 +632,17 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
     p.mat = mi;
     p.type = sd->obj_type[i];
     p.q = from_d(sd->obj_pos + 3 * (size_t)i);
+    if (!finite3(p.q)) return not_finite(i);
     if (p.type == OBJ_SPHERE) {
       p.r = sd->obj_r ? sd->obj_r[i] : 0;
+      if (!std::isfinite((float)p.r)) return not_finite(i);
       if (p.r < 0) any_negative = true;
       make_sphere(p);
     } else if (p.type == OBJ_PLANE || p.type == OBJ_QUAD) {
       if (!sd->obj_u || !sd->obj_v) { err = "plane/quad without u/v"; return RT_ERR_INVALID_ARGUMENT; }
       p.u = from_d(sd->obj_u + 3 * (size_t)i);
       p.v = from_d(sd->obj_v + 3 * (size_t)i);
+      if (!finite3(p.u) || !finite3(p.v)) return not_finite(i);
       make_planar(p);
       S.planar_any = 1;
     } else {

@@ -149,6 +149,17 @@ def test_scene_validate_raises_the_reference_errors():
     bad["objects"][0]["type"] = "torus"
     with pytest.raises(RaytracerError, match="Unknown object type"):
         validateScene(bad)
+    # not in the reference (it would render NaN): geometry that is not finite in FP32 is refused, for every tree kind
+    for field, value in (("pos", [0.0, 1e300, 0.0]), ("r", float("nan")), ("pos", [float("inf"), 0.0, 0.0])):
+        for bvh in ("list", "sah", "reference"):
+            bad = generateCornellSceneData()
+            bad["objects"][6][field] = value
+            with pytest.raises(RaytracerError, match="non-finite geometry"):
+                validateScene(bad, {"bvh": bvh})
+    bad = generateCornellSceneData()
+    bad["objects"][0]["u"] = [0.0, float("inf"), 0.0]
+    with pytest.raises(RaytracerError, match="non-finite geometry"):
+        validateScene(bad)
 
 
 def test_product_package_never_touches_the_oracle():
