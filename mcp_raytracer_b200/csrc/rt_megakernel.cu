@@ -1396,8 +1396,9 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       }
 #endif
       if (sorted_list) {
-        static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_LIST>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                              57); // 3 CTAs x 43.4 KB fit the 132 KB split; the rest stays L1
+        // 3 CTAs x 43.4 KB fit the 132 KB split; the rest stays L1.  Function attributes are per device, and one
+        // process may drive several GPUs, so this is set at every launch (microseconds, once per render).
+        const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_LIST>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
         return launch_persistent(k_render_sorted<BVH_LIST>, S, R, work, sms, st);
       }
@@ -1408,7 +1409,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       // 64-byte slots; final tree layout): 11.7 / 15.2 ms at 8 k slots (8 000 spheres), 19.2 / 18.1 at 20 k,
       // 27.5 / 22.9 at 48.5 k: regenerating paths mid-traversal pays once lanes diverge by many node visits.
       if (sorted_list && (S.n_nodes < kTravNodes || no_trav)) {
-        static const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
+        const cudaError_t carve = cudaFuncSetAttribute(k_render_sorted<BVH_SAH>, cudaFuncAttributePreferredSharedMemoryCarveout, 57);
         if (carve != cudaSuccess) return carve;
         return launch_persistent(k_render_sorted<BVH_SAH>, S, R, work, sms, st);
       }
