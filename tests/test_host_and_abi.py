@@ -138,6 +138,35 @@ def test_scene_compiler_structures_are_sound():
     assert validateScene(scenes["rain"])["n_prefix"] == 0        # big scenes keep everything in the tree
 
 
+def test_scene_compiler_survives_degenerate_scenes():
+    """Inputs a JSON client can send and no generator produces: coincident / collinear / nested primitives (no
+    centroid spread for the SAH bins), zero radii, zero-area quads, coordinates near the ends of the FP32 range
+    (box areas overflow to inf), twenty decades of scale in one scene.  Every tree must still be sound."""
+    from mcp_raytracer_b200 import validateScene
+
+    rng = np.random.default_rng(0)
+    m = {"type": "lambert", "color": [0.7, 0.6, 0.5]}
+    sph = lambda p, r: {"type": "sphere", "pos": [float(x) for x in p], "r": float(r), "material": m}  # noqa: E731
+    cases = {
+        "coincident": [sph([1, 2, 3], 0.5) for _ in range(3000)],
+        "collinear": [sph([i, 0, 0], 0.1) for i in range(3000)],
+        "nested": [sph([0, 0, 0], 1 + i * 1e-3) for i in range(2000)],
+        "zero_radius": [sph(rng.random(3), 0.0) for _ in range(500)],
+        "fp32_max": [sph(rng.random(3) * 3e38, 1e37) for _ in range(500)],
+        "fp32_tiny": [sph(rng.random(3) * 1e-30, 1e-35) for _ in range(500)],
+        "scales": [sph(rng.random(3) * 10 ** rng.uniform(-20, 20), 10 ** rng.uniform(-20, 20)) for _ in range(2000)],
+        "zero_area_quads": [{"type": "quad", "pos": rng.random(3).tolist(), "u": [0, 0, 0], "v": [0, 0, 0], "material": m}
+                            for _ in range(200)],
+        "inverted_boxes": [sph(rng.random(3) * 5, -0.1) for _ in range(300)],
+    }
+    for name, objs in cases.items():
+        sd = {"type": "custom", "camera": {"vfov": 60, "from": [0.3, 1.1, 9], "at": [0, 0, 0]}, "objects": objs}
+        for bvh in ("auto", "sah", "reference"):
+            rep = validateScene(sd, {"bvh": bvh})
+            assert rep["errors"] == 0 and rep["n_slots"] == len(objs), (name, bvh, rep)
+            assert rep["max_depth"] <= (42 if rep["bvh_kind"] == 2 else 60), (name, bvh, rep)
+
+
 def test_scene_validate_raises_the_reference_errors():
     from mcp_raytracer_b200 import RaytracerError, generateCornellSceneData, validateScene
 
