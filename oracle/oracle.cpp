@@ -235,6 +235,10 @@ struct Ray {
 struct Interval {
   double mn, mx;
   bool surrounds(double x) const { return mn < x && x < mx; } // interval.ts:51-53 (strict)
+  // the rest of the type (interval.ts:33-64); only `surrounds` is called on the render path
+  double size() const { return mx - mn; }
+  bool contains(double x) const { return mn <= x && x <= mx; }
+  double clamp(double x) const { return x < mn ? mn : (x > mx ? mx : x); }
 };
 struct AABB {
   V3 mn, mx;
@@ -1355,6 +1359,59 @@ int orc_pixel_converged(void* cam, int samples, double sumIll, double sumIll2) {
   PixelStats p;
   p.samples = samples; p.sumIll = sumIll; p.sumIll2 = sumIll2;
   return ((Camera*)cam)->pixelConverged(p);
+}
+
+// The vector / ray / interval layer on its own (vec3.ts, ray.ts:25-28, interval.ts), so the reference's
+// tests/geometry/{vec3,ray,interval}.test.ts vectors can be replayed against it.
+// op: 0 negate, 1 add, 2 subtract, 3 multiply(s), 4 multiplyVec, 5 divide(s), 6 cross, 7 unitVector -> out3;
+//     8 lengthSquared, 9 length, 10 dot, 11 nearZero (vec3.ts:215-221), 12 illuminance -> return value.
+double orc_vec3_op(int op, const double* a, const double* b, double s, float* out3) {
+  const V3 A = mk(a[0], a[1], a[2]);
+  const V3 B = b ? mk(b[0], b[1], b[2]) : mk(0, 0, 0);
+  V3 r = mk(0, 0, 0);
+  double v = 0;
+  switch (op) {
+    case 0: r = neg(A); break;
+    case 1: r = add(A, B); break;
+    case 2: r = sub(A, B); break;
+    case 3: r = scale(A, s); break;
+    case 4: r = mulv(A, B); break;
+    case 5: r = divs(A, s); break;
+    case 6: r = cross(A, B); break;
+    case 7: r = unit(A); break;
+    case 8: v = len2(A); break;
+    case 9: v = len(A); break;
+    case 10: v = dot(A, B); break;
+    case 11: v = (std::fabs((double)A.x) < 1e-8 && std::fabs((double)A.y) < 1e-8 && std::fabs((double)A.z) < 1e-8) ? 1 : 0; break;
+    case 12: v = illuminance(A); break;
+    default: return std::nan("");
+  }
+  if (out3) { out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+  return v;
+}
+void orc_ray_at(const double* o, const double* d, double t, float* out3) {
+  Ray r{mk(o[0], o[1], o[2]), mk(d[0], d[1], d[2])};
+  V3 p = r.at(t);
+  out3[0] = p.x; out3[1] = p.y; out3[2] = p.z;
+}
+// op: 0 size, 1 contains, 2 surrounds, 3 clamp
+double orc_interval_op(int op, double mn, double mx, double x) {
+  Interval iv{mn, mx};
+  switch (op) {
+    case 0: return iv.size();
+    case 1: return iv.contains(x) ? 1 : 0;
+    case 2: return iv.surrounds(x) ? 1 : 0;
+    case 3: return iv.clamp(x);
+    default: return std::nan("");
+  }
+}
+// kind: 0 Vec3.random(mn, mx) (vec3.ts:272-278), 1 randomInUnitSphere (:285-292), 2 randomInUnitDisk (:357-364)
+void orc_sample_vec3(int kind, uint64_t seed, double mn, double mx, int cnt, float* out) {
+  Rng g; g.mode = 1; g.seed_sequential(seed);
+  for (int i = 0; i < cnt; ++i) {
+    V3 x = kind == 0 ? randomVec(g, mn, mx) : (kind == 1 ? randomInUnitSphere(g) : randomInUnitDisk(g));
+    out[3 * i] = x.x; out[3 * i + 1] = x.y; out[3 * i + 2] = x.z;
+  }
 }
 
 } // extern "C"

@@ -89,6 +89,12 @@ def lib() -> C.CDLL:
         L.orc_material_scatter.argtypes = [C.POINTER(rt_scene_desc), C.c_int, dp, dp, dp, dp, C.c_int, C.c_uint64, C.c_uint32, dp, fp]
         L.orc_write_color.argtypes = [dp, C.POINTER(C.c_uint8)]
         L.orc_pixel_converged.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        L.orc_vec3_op.argtypes = [C.c_int, dp, dp, C.c_double, fp]
+        L.orc_vec3_op.restype = C.c_double
+        L.orc_ray_at.argtypes = [dp, dp, C.c_double, fp]
+        L.orc_interval_op.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+        L.orc_interval_op.restype = C.c_double
+        L.orc_sample_vec3.argtypes = [C.c_int, C.c_uint64, C.c_double, C.c_double, C.c_int, fp]
         _LIB = L
     return _LIB
 

@@ -514,3 +514,110 @@ def test_pixel_converged_rule():  # camera.ts:348-368
     assert pc(c.h, 10, 10.0, 19.0) == 0
     c0 = ob.OracleCamera(_empty_world(), {"samples": 100, "aTolerance": 0.0})
     assert pc(c0.h, 10, 10.0, 10.0) == 0        # adaptive off
+
+
+# ---------------------------------------------------------------- Vec3 / Ray / Interval on their own
+def _v3(op, a, b=None, s=0.0):
+    out = (C.c_float * 3)()
+    val = lib().orc_vec3_op(op, d3(a), d3(b) if b is not None else None, float(s), out)
+    return list(out), val
+
+
+NEG, ADD, SUB, MUL, MULV, DIV, CROSS, UNIT, LEN2, LEN, DOT, NEARZERO, ILLUM = range(13)
+
+
+def test_vec3_operator_methods():  # tests/geometry/vec3.test.ts:34-58 (exact on small integers)
+    v1, v2 = (1, 2, 3), (4, 5, 6)
+    assert _v3(NEG, v1)[0] == [-1, -2, -3]
+    assert _v3(ADD, v1, v2)[0] == [5, 7, 9]
+    assert _v3(SUB, v1, v2)[0] == [-3, -3, -3] and _v3(SUB, v2, v1)[0] == [3, 3, 3]
+    assert _v3(MUL, v1, s=2)[0] == [2, 4, 6] and _v3(MUL, v1, s=0)[0] == [0, 0, 0]
+    assert _v3(MULV, v1, v2)[0] == [4, 10, 18]
+    assert _v3(DIV, (2, 4, 6), s=2)[0] == [1, 2, 3]
+    # vec3.ts:60-70: negate never yields -0 (toEqual distinguishes +0 / -0 in Jest)
+    assert all(math.copysign(1.0, x) == 1.0 for x in _v3(NEG, (0, 0, 0))[0])
+
+
+def test_vec3_magnitude_dot_cross_unit():  # tests/geometry/vec3.test.ts:81-111, :183-218
+    v = (3, 4, 0)
+    assert _v3(LEN2, v)[1] == 25 and _v3(LEN2, (0, 0, 0))[1] == 0
+    assert _v3(LEN, v)[1] == pytest.approx(5, abs=5e-3) and _v3(LEN, (0, 0, 0))[1] == 0
+    assert _v3(LEN, (1, 1, 1))[1] == pytest.approx(math.sqrt(3), abs=5e-3)
+    assert _v3(DOT, v, (4, -5, 6))[1] == -8
+    assert _v3(CROSS, v, (0, 0, 1))[0] == [4, -3, 0]
+    u = _v3(UNIT, v)[0]
+    assert u == pytest.approx([0.6, 0.8, 0.0], abs=5e-3) and _v3(LEN, u)[1] == pytest.approx(1, abs=5e-3)
+    v1, v2 = (1, 2, 3), (4, -5, 6)
+    i, j, k = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+    assert _v3(DOT, v1, v2)[1] == 12 and _v3(DOT, v1, (0, 0, 0))[1] == 0
+    assert _v3(DOT, i, j)[1] == 0 and _v3(DOT, i, i)[1] == 1
+    assert _v3(CROSS, v1, v2)[0] == [27, 6, -13]
+    assert _v3(CROSS, i, j)[0] == list(k) and _v3(CROSS, j, i)[0] == [0, 0, -1]
+    assert _v3(CROSS, v1, v1)[0] == [0, 0, 0] and _v3(CROSS, v1, (0, 0, 0))[0] == [0, 0, 0]
+    assert _v3(UNIT, i)[0] == [1, 0, 0]
+
+
+def test_vec3_near_zero():  # tests/geometry/vec3.test.ts:162-171
+    assert _v3(NEARZERO, (1e-9, -1e-9, 1e-9))[1] == 1
+    assert _v3(NEARZERO, (0.001, 0.001, 0.001))[1] == 0
+    assert _v3(NEARZERO, (0, 0, 0))[1] == 1
+
+
+def test_vec3_results_are_stored_in_fp32():
+    """gl-matrix ARRAY_TYPE = Float32Array: every vector result is rounded to FP32 on store, scalars stay FP64
+    (SURVEY.md App. A.1).  Asserted by NO reference test ("parity unpinned" for this aspect): this pins the
+    oracle to the documented model so it cannot drift."""
+    a, b = (0.1, 0.2, 0.3), (0.7, 0.11, 1e-9)
+    fa, fb = np.float32(a), np.float32(b)
+    got = _v3(ADD, a, b)[0]
+    want = (fa.astype(np.float64) + fb.astype(np.float64)).astype(np.float32)  # FP64 sum of the FP32 inputs, one rounding
+    assert got == [float(x) for x in want]
+    assert _v3(DOT, a, b)[1] == float(np.sum(fa.astype(np.float64) * fb.astype(np.float64)[[0, 1, 2]]))  # FP64, not rounded
+    d = _v3(DOT, a, b)[1]
+    assert d != float(np.float32(d))  # i.e. really more than FP32 precision
+    u = _v3(UNIT, a)[0]
+    inv = 1.0 / math.sqrt(float(np.sum(fa.astype(np.float64) ** 2)))  # gl-matrix normalize: multiply by 1/sqrt(len^2)
+    assert u == [float(np.float32(float(x) * inv)) for x in fa]
+    assert _v3(UNIT, (0, 0, 0))[0] == [0, 0, 0]  # gl-matrix leaves the zero vector at zero
+
+
+def test_vec3_random_generators():  # tests/geometry/vec3.test.ts:115-159 (the two used on the render path) + unit disk
+    n = 2000
+    out = (C.c_float * (3 * n))()
+    lib().orc_sample_vec3(0, 5, -1.0, 1.0, n, out)
+    v = np.array(out, np.float64).reshape(n, 3)
+    assert v.min() >= -1 and v.max() <= 1 and abs(v.mean()) < 0.05
+    lib().orc_sample_vec3(1, 6, 0.0, 0.0, n, out)
+    v = np.array(out, np.float64).reshape(n, 3)
+    assert np.all((v ** 2).sum(1) <= 1) and np.abs(v.mean(0)).max() < 0.05
+    # uniform in the ball: P(|p| < 0.5) = 1/8
+    assert abs(np.mean((v ** 2).sum(1) < 0.25) - 0.125) < 0.03
+    lib().orc_sample_vec3(2, 7, 0.0, 0.0, n, out)  # vec3.ts:357-364, used by the defocus disk (camera.ts:197-207)
+    v = np.array(out, np.float64).reshape(n, 3)
+    assert np.all(v[:, 2] == 0) and np.all((v ** 2).sum(1) < 1)
+
+
+def test_ray_at():  # tests/geometry/ray.test.ts:41-87
+    def at(t):
+        out = (C.c_float * 3)()
+        lib().orc_ray_at(d3((1, 2, 3)), d3((4, 5, 6)), t, out)
+        return list(out)
+    assert at(0) == [1, 2, 3]
+    assert at(1) == [5, 7, 9]
+    assert at(0.5) == [3, 4.5, 6]
+    assert at(-1) == [-3, -3, -3]
+
+
+def test_interval():  # tests/geometry/interval.test.ts:27-99
+    iv = lib().orc_interval_op
+    SIZE, CONTAINS, SURROUNDS, CLAMP = range(4)
+    assert iv(SIZE, 1, 5, 0) == 4 and iv(SIZE, -2, 3, 0) == 5
+    assert iv(SIZE, INF, -INF, 0) < 0 and iv(SIZE, -INF, INF, 0) == INF          # EMPTY / UNIVERSE
+    assert all(iv(CONTAINS, 1, 5, x) == 1 for x in (1, 3, 5)) and all(iv(CONTAINS, 1, 5, x) == 0 for x in (0.9, 5.1))
+    assert all(iv(CONTAINS, -INF, INF, x) == 1 for x in (0, -1e10, 1e10)) and iv(CONTAINS, INF, -INF, 0) == 0
+    assert all(iv(SURROUNDS, 1, 5, x) == 1 for x in (1.1, 3, 4.9))
+    assert all(iv(SURROUNDS, 1, 5, x) == 0 for x in (1, 5, 0.9, 5.1))             # strict: what every hit test relies on
+    assert all(iv(SURROUNDS, -INF, INF, x) == 1 for x in (0, -1e10, 1e10)) and iv(SURROUNDS, INF, -INF, 0) == 0
+    assert [iv(CLAMP, 1, 5, x) for x in (3, 1, 5, 0, -10, 6, 100)] == [3, 1, 5, 1, 1, 5, 5]
+    assert iv(CLAMP, -INF, INF, 100) == 100 and iv(CLAMP, -INF, INF, -100) == -100
+    assert iv(CLAMP, INF, -INF, 0) == INF
