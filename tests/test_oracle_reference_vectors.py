@@ -621,3 +621,25 @@ def test_interval():  # tests/geometry/interval.test.ts:27-99
     assert [iv(CLAMP, 1, 5, x) for x in (3, 1, 5, 0, -10, 6, 100)] == [3, 1, 5, 1, 1, 5, 5]
     assert iv(CLAMP, -INF, INF, 100) == 100 and iv(CLAMP, -INF, INF, -100) == -100
     assert iv(CLAMP, INF, -INF, 0) == INF
+
+
+def test_ray_color_edge_cases():  # camera.test.ts:441-487 (PDF materials), :518-590 (roulette), :658-720 (attenuation 0 / 2)
+    """The reference asserts "does not throw, components >= 0"; the restatement adds what follows from the code:
+    a black Lambertian returns exactly zero radiance, an albedo of 2 stays finite (continuation probability is
+    capped at 0.95, camera.ts:236), and every path ends within `depth` bounces."""
+    def cam(albedo, **render):
+        sd = _sphere_scene([((0, 0, -1), 0.5)])
+        sd["materials"][0]["material"]["color"] = [albedo] * 3
+        return ob.OracleCamera(sd, {"width": 10, "aspect": 1.0, "samples": 1, **render})
+    for s in range(64):
+        rgb, bounces = cam(0.0, roulette=True, rouletteDepth=1).ray_color((0, 0, 0), (0, 0, -1), sample=s)
+        assert np.all(rgb == 0) and 1 <= bounces <= 100
+        rgb, bounces = cam(2.0, roulette=True, rouletteDepth=1, depth=40).ray_color((0, 0, 0), (0, 0, -1), sample=s)
+        assert np.all(np.isfinite(rgb)) and np.all(rgb >= 0) and bounces <= 40
+        rgb, bounces = cam(0.5, roulette=True, rouletteDepth=5).ray_color((0, 0, 0), (0, 0, -1), sample=s)
+        assert np.all(np.isfinite(rgb)) and np.all(rgb >= 0) and bounces >= 1
+    # roulette off: only the depth cut ends a path that keeps hitting (camera.ts:228), and it returns black
+    inside = _sphere_scene([((0, 0, 0), 5.0)])  # the camera sits inside a closed grey sphere: no ray ever escapes
+    c = ob.OracleCamera(inside, {"width": 10, "aspect": 1.0, "samples": 1, "roulette": False, "depth": 7})
+    rgb, bounces = c.ray_color((0, 0, 0), (0, 0, -1))
+    assert bounces == 7 and np.all(rgb == 0)
