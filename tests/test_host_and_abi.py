@@ -138,6 +138,24 @@ def test_scene_compiler_structures_are_sound():
     assert validateScene(scenes["rain"])["n_prefix"] == 0        # big scenes keep everything in the tree
 
 
+def test_reference_topology_matches_the_oracles_tree():
+    """RT_BVH_REFERENCE flattens the reference's own median-split tree (bvh.ts:34-102): same depth as the tree the
+    oracle builds from the reference's rules, and as many leaves as that (full binary) tree has leaf-holding nodes."""
+    import oracle_binding as ob
+    from mcp_raytracer_b200 import (generateCornellSceneData, generateDefaultSceneData, generateRainSceneData,
+                                    generateSpheresSceneData, generateWeekendFinalSceneData, validateScene)
+
+    scenes = [generateCornellSceneData(), generateDefaultSceneData(), generateSpheresSceneData({"count": 100, "seed": 12345}),
+              generateWeekendFinalSceneData(), generateRainSceneData({"count": 5000, "seed": 1, "sphereRadius": 0.01})]
+    scenes += [_mixed_scene(seed, n) for seed, n in ((1, 5), (2, 14), (3, 40), (4, 300), (6, 5000))]
+    for sd in scenes:
+        o = ob.OracleCamera(sd, {"width": 16, "samples": 1})
+        rep = validateScene(sd, {"bvh": "reference"})
+        assert rep["errors"] == 0 and rep["bvh_kind"] == 1
+        assert rep["max_depth"] == o.bvh_depth, (len(sd["objects"]), rep, o.bvh_depth)
+        assert rep["n_leaves"] == (o.bvh_nodes + 1) // 2, (len(sd["objects"]), rep, o.bvh_nodes)
+
+
 def test_scene_compiler_survives_degenerate_scenes():
     """Inputs a JSON client can send and no generator produces: coincident / collinear / nested primitives (no
     centroid spread for the SAH bins), zero radii, zero-area quads, coordinates near the ends of the FP32 range
