@@ -219,6 +219,48 @@ rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint
 rt_status rt_camera_trace_primary(rt_camera* cam, const rt_region* region, int32_t* obj_id,
                                   float* t, float* normal, uint8_t* front_face);
 
+/* ---- per-function parity hooks ----------------------------------------------------------------
+ * Each call runs ONE device function of the render path (the same code the render kernels inline) on
+ * `n` explicit records, with the uniforms `Math.random()` would return given by the caller: RT_DEBUG_UNIFORMS
+ * doubles per record, consumed in the reference's draw order, each rounded to FP32 (give k / 2^24 values to
+ * feed the CPU oracle bit-identical numbers); draws past the end read 0.5.  Host pointers; synchronous.
+ * Used by tests/test_gpu_functions.py against the reference's own Jest vectors; not on the render path. */
+#define RT_DEBUG_UNIFORMS 16
+typedef struct rt_debug_hit { /* rIn + HitRecord — src/geometry/hittable.ts:9-18 */
+  double ray_origin[3], ray_dir[3];
+  double p[3], normal[3];  /* rec.p, rec.normal (face-forwarded unit normal) */
+  int32_t front_face;      /* rec.frontFace */
+  int32_t reserved;
+} rt_debug_hit;
+typedef struct rt_debug_scatter_out { /* ScatterResult | null — src/materials/material.ts:14-23 */
+  int32_t kind;            /* 0 = null (absorbed, or a light), 1 = `scattered` ray (specular), 2 = `pdf` (cosine pdf about rec.normal) */
+  int32_t uniforms_used;
+  float attenuation[3];
+  float dir[3];            /* kind 1: scattered.direction */
+  float emitted[3];        /* material.emitted(rec) */
+} rt_debug_scatter_out;
+/* material.scatter + material.emitted of SceneData.objects[object_index].material at each hit
+ * (src/materials/{lambertian,metal,dielectric,diffuseLight,layeredMaterial,mixedMaterial}.ts) */
+rt_status rt_debug_scatter(rt_camera* cam, int32_t object_index, int32_t n, const rt_debug_hit* hits,
+                           const double* uniforms, rt_debug_scatter_out* out);
+/* Camera.getRay(i, j) — src/camera.ts:176-210.  ij [n][2]; ray_out [n][6] = origin.xyz, direction.xyz
+ * (direction NOT normalised, like the reference); used [n] = uniforms consumed (optional). */
+rt_status rt_debug_get_ray(rt_camera* cam, int32_t n, const int32_t* ij, const double* uniforms,
+                           float* ray_out, int32_t* used);
+/* lights[light_index].pdfValue(origin, direction) — src/entities/quad.ts:123-140, sphere.ts:106-131.
+ * light_index counts the scene's lights in SceneData.objects order (src/scenes/scenes.ts:74-79). */
+rt_status rt_debug_light_pdf(rt_camera* cam, int32_t light_index, int32_t n, const double* origin,
+                             const double* direction, float* value);
+/* lights[light_index].pdfRandomVec(origin) — src/entities/quad.ts:148-158, sphere.ts:140-147 +
+ * src/geometry/vec3.ts:345-351; two uniforms per record.  out [n][3]. */
+rt_status rt_debug_light_random_vec(rt_camera* cam, int32_t light_index, int32_t n, const double* origin,
+                                    const double* uniforms, float* out);
+/* The diffuse branch of rayColor — src/camera.ts:285-308 with MixturePDF (src/geometry/pdf.ts:57-99), CosinePDF
+ * (:32-51) and ONBasis (src/geometry/onbasis.ts:18-51): three uniforms per record (component select, r1, r2).
+ * out [n][6] = direction.xyz, mixture pdf value, scatter pdf value, continues (pdf value > 0.0001). */
+rt_status rt_debug_diffuse_bounce(rt_camera* cam, int32_t n, const double* p, const double* normal,
+                                  const double* uniforms, float* out);
+
 /* ---- misc ---- */
 const char* rt_last_error(void);
 int32_t rt_device_count(void);

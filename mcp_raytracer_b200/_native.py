@@ -22,6 +22,7 @@ EXPORTS = [
     "rt_camera_render_region", "rt_camera_render", "rt_camera_render_region_device",
     "rt_camera_render_moments", "rt_camera_trace_primary", "rt_last_error", "rt_device_count",
     "rt_abi_version", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
+    "rt_debug_scatter", "rt_debug_get_ray", "rt_debug_light_pdf", "rt_debug_light_random_vec", "rt_debug_diffuse_bounce",
 ]
 
 STATUS_NAMES = {
@@ -70,6 +71,12 @@ def lib() -> C.CDLL:
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.rt_trim_device_cache.restype = C.c_uint64
     L.rt_scene_validate.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), vp]
+    i32 = C.c_int32
+    L.rt_debug_scatter.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.rt_debug_get_ray.argtypes = [vp, i32, vp, vp, vp, vp]
+    L.rt_debug_light_pdf.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.rt_debug_light_random_vec.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.rt_debug_diffuse_bounce.argtypes = [vp, i32, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -200,6 +200,63 @@ class Camera:
         return ids, t, nrm, ff
 
 
+    # -- per-function parity hooks (rt_debug_*): one device function of the render path on explicit inputs --
+    DEBUG_UNIFORMS = 16
+
+    def _uniforms(self, uniforms, n: int) -> np.ndarray:
+        u = np.full((n, self.DEBUG_UNIFORMS), 0.5, np.float64)
+        a = np.asarray(uniforms, np.float64).reshape(n, -1) if n else np.zeros((0, 0))
+        u[:, :a.shape[1]] = a[:, :self.DEBUG_UNIFORMS]
+        return np.ascontiguousarray(u)
+
+    def debugScatter(self, objectIndex: int, rayOrigin, rayDir, p, normal, frontFace, uniforms):
+        """material.scatter + material.emitted of objects[objectIndex].material at n synthetic hits.
+        Returns dict of arrays: kind (0 null, 1 scattered ray, 2 pdf), used, attenuation, dir, emitted."""
+        ro, rd, pp, nn = (np.ascontiguousarray(np.atleast_2d(x), np.float64) for x in (rayOrigin, rayDir, p, normal))
+        n = ro.shape[0]
+        hits = np.zeros((n, 13), np.float64)  # rt_debug_hit: 12 doubles + two int32
+        hits[:, 0:3], hits[:, 3:6], hits[:, 6:9], hits[:, 9:12] = ro, rd, pp, nn
+        ff = np.zeros((n, 2), np.int32)
+        ff[:, 0] = np.asarray(frontFace, np.int32).reshape(n)
+        hits[:, 12] = ff.view(np.float64).reshape(n)
+        u = self._uniforms(uniforms, n)
+        out = np.zeros((n, 11), np.float32)  # rt_debug_scatter_out: 2 int32 + 9 float
+        self._check(_native.lib().rt_debug_scatter(self._h, int(objectIndex), n, hits.ctypes.data, u.ctypes.data, out.ctypes.data))
+        ints = out[:, 0:2].copy().view(np.int32)
+        return {"kind": ints[:, 0], "used": ints[:, 1], "attenuation": out[:, 2:5], "dir": out[:, 5:8], "emitted": out[:, 8:11]}
+
+    def debugGetRay(self, ij, uniforms):
+        """Camera.getRay(i, j) for n pixels: (origin [n,3], direction [n,3], uniforms used [n])."""
+        a = np.ascontiguousarray(np.atleast_2d(ij), np.int32)
+        n = a.shape[0]
+        u = self._uniforms(uniforms, n)
+        out = np.zeros((n, 6), np.float32)
+        used = np.zeros(n, np.int32)
+        self._check(_native.lib().rt_debug_get_ray(self._h, n, a.ctypes.data, u.ctypes.data, out.ctypes.data, used.ctypes.data))
+        return out[:, 0:3], out[:, 3:6], used
+
+    def debugLightPdf(self, lightIndex: int, origin, direction) -> np.ndarray:
+        o, d = (np.ascontiguousarray(np.atleast_2d(x), np.float64) for x in (origin, direction))
+        out = np.zeros(o.shape[0], np.float32)
+        self._check(_native.lib().rt_debug_light_pdf(self._h, int(lightIndex), o.shape[0], o.ctypes.data, d.ctypes.data, out.ctypes.data))
+        return out
+
+    def debugLightRandomVec(self, lightIndex: int, origin, uniforms) -> np.ndarray:
+        o = np.ascontiguousarray(np.atleast_2d(origin), np.float64)
+        u = self._uniforms(uniforms, o.shape[0])
+        out = np.zeros((o.shape[0], 3), np.float32)
+        self._check(_native.lib().rt_debug_light_random_vec(self._h, int(lightIndex), o.shape[0], o.ctypes.data, u.ctypes.data, out.ctypes.data))
+        return out
+
+    def debugDiffuseBounce(self, p, normal, uniforms) -> np.ndarray:
+        """camera.ts:285-308 at n hit points: [n,6] = direction, mixture pdf value, scatter pdf value, continues."""
+        pp, nn = (np.ascontiguousarray(np.atleast_2d(x), np.float64) for x in (p, normal))
+        u = self._uniforms(uniforms, pp.shape[0])
+        out = np.zeros((pp.shape[0], 6), np.float32)
+        self._check(_native.lib().rt_debug_diffuse_bounce(self._h, pp.shape[0], pp.ctypes.data, nn.ctypes.data, u.ctypes.data, out.ctypes.data))
+        return out
+
+
 def createCameraFromSceneData(sceneData: Dict[str, Any], renderOptions: Optional[Dict[str, Any]] = None) -> Camera:
     """src/scenes/scenes.ts:60-104"""
     return Camera(sceneData, None, renderOptions)

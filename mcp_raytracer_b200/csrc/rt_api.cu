@@ -27,6 +27,12 @@ cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* 
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
 cudaError_t launch_render_wavefront(const DevScene& S, const RenderParams& R, WfHost& H, int sms, cudaStream_t st, int* launches);
 cudaError_t launch_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches, cudaStream_t st);
+// per-function parity hooks (rt_debug.cuh)
+cudaError_t launch_debug_scatter(const DevScene& S, int root, int n, const void* hits, const float* uniforms, void* out, cudaStream_t st);
+cudaError_t launch_debug_get_ray(const DevScene& S, int n, const int* ij, const float* uniforms, float* out, int* used, cudaStream_t st);
+cudaError_t launch_debug_light_pdf(const DevScene& S, int light, int n, const float* origin, const float* dir, float* value, cudaStream_t st);
+cudaError_t launch_debug_light_random(const DevScene& S, int light, int n, const float* origin, const float* uniforms, float* out, cudaStream_t st);
+cudaError_t launch_debug_diffuse(const DevScene& S, int n, const float* p, const float* nrm, const float* uniforms, float* out, cudaStream_t st);
 } // namespace rt
 
 using namespace rt;
@@ -36,6 +42,11 @@ static rt_status fail(rt_status st, const std::string& msg) {
   g_err = msg;
   return st;
 }
+// No C++ exception crosses the ABI (include/rt_b200.h): every extern "C" body that allocates host memory sits between these.
+#define RT_GUARD_BEGIN try {
+#define RT_GUARD_END                                                                                   \
+  } catch (const std::bad_alloc&) { return fail(RT_ERR_INVALID_ARGUMENT, "out of host memory"); }      \
+  catch (const std::exception& e) { return fail(RT_ERR_INVALID_ARGUMENT, std::string("internal error: ") + e.what()); }
 #define CU(call)                                                                                      \
   do {                                                                                                \
     cudaError_t e_ = (call);                                                                          \
@@ -248,6 +259,7 @@ uint64_t rt_trim_device_cache(void) {
 
 // Host-only: compile the scene like rt_camera_create and check the structure the kernels will walk.
 rt_status rt_scene_validate(const rt_scene_desc* scene, const rt_render_opts* opts, rt_scene_report* rep) {
+  RT_GUARD_BEGIN
   if (!scene || !opts || !rep) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
   HostScene hs;
   std::string err;
@@ -354,6 +366,7 @@ rt_status rt_scene_validate(const rt_scene_desc* scene, const rt_render_opts* op
   for (int s = 0; s < n; ++s) if (seen_slot[s] != 1) ++errors;
   rep->errors = errors;
   return RT_OK;
+  RT_GUARD_END
 }
 int32_t rt_device_count(void) {
   int n = 0;
@@ -364,10 +377,12 @@ int32_t rt_device_count(void) {
 rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opts, rt_camera** out) {
   if (!scene || !opts || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
   *out = nullptr;
+  rt_camera* c = nullptr;
+  try {
   auto t0 = std::chrono::steady_clock::now();
   // validate + compile first: scene errors are reported even on a box without a GPU,
   // exactly like the reference throws before rendering anything
-  rt_camera* c = new rt_camera();
+  c = new rt_camera();
   std::string err;
   rt_status st = compile_scene(scene, opts, c->hs, err);
   if (st != RT_OK) { delete c; return fail(st, err); }
@@ -436,6 +451,10 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   c->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   *out = c;
   return RT_OK;
+  } catch (const std::exception& e) { // std::bad_alloc on a huge scene: nothing half-built stays behind
+    if (c) free_camera(c);
+    return fail(RT_ERR_INVALID_ARGUMENT, std::string("rt_camera_create: ") + e.what());
+  }
 }
 
 rt_status rt_camera_destroy(rt_camera* cam) {
@@ -538,7 +557,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
   if (P.x1 > P.x0 && P.y1 > P.y0) {
     render_tile_grid(P, &P.tiles_x, &P.tiles_y);
     if (render_needs_full(c->ds, P)) P.chunks = 1;
-    else if (c->chunks > 0) P.chunks = c->chunks;
+    else if (c->chunks > 0) P.chunks = std::min(c->chunks, std::max(1, c->hs.cam.samples)); // never an empty chunk (k_render_sorted skips them)
     else {
       // Sample chunks per pixel: enough (8x4 block, chunk) warp items that the blocks this GPU owns
       // keep it busy for >= 16 rounds of resident warps, so the tail of the render stays ~1/32 of it
@@ -605,6 +624,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
 
 rt_status rt_camera_render_region_device(rt_camera* c, const rt_region* region, uint8_t* rgb8_dev, float* linear_dev,
                                          float* moments_dev, rt_stats* stats_dev) {
+  RT_GUARD_BEGIN
   if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
   DeviceGuard g(c->device);
   RenderParams P;
@@ -613,10 +633,12 @@ rt_status rt_camera_render_region_device(rt_camera* c, const rt_region* region, 
   P.rgb8 = rgb8_dev; P.linear = linear_dev; P.moments = moments_dev;
   int launches = 0;
   return enqueue_render(c, P, stats_dev, &launches);
+  RT_GUARD_END
 }
 
 static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb8, size_t rgb8_len, float* linear,
                              float* moments, rt_stats* stats) {
+  RT_GUARD_BEGIN
   if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
   const int W = c->hs.image_width, H = c->hs.image_height;
   const size_t npx = (size_t)W * H;
@@ -685,6 +707,7 @@ static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb
     stats->kernel_launches = launches;
   }
   return RT_OK;
+  RT_GUARD_END
 }
 
 rt_status rt_camera_render_region(rt_camera* cam, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
@@ -759,6 +782,135 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
   *tflops = best;
   if (sm_clock_mhz) *sm_clock_mhz = khz / 1000.0;
   return RT_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// per-function parity hooks: stage the records (rounded to FP32 where `Vec3.create` would round them,
+// src/geometry/vec3.ts:263), run one thread per record, copy the answers back.  Synchronous.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct DbgBuf { // device scratch of one hook call, returned to the cache on scope exit
+  std::vector<void*> ptrs;
+  ~DbgBuf() { for (void* p : ptrs) dev_free(p); }
+  template <class T>
+  cudaError_t up(const std::vector<T>& h, T** d) {
+    cudaError_t e = dev_alloc(d, std::max<size_t>(h.size(), 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(*d);
+    return h.empty() ? cudaSuccess : cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+  }
+  template <class T>
+  cudaError_t out(size_t n, T** d) {
+    cudaError_t e = dev_alloc(d, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(*d);
+    return e;
+  }
+};
+std::vector<float> to_f32(const double* p, size_t n) {
+  std::vector<float> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (float)p[i];
+  return v;
+}
+struct DbgHitH { float ro[3], rd[3], p[3], n[3]; int front, pad; }; // = rt::DbgHit (rt_debug.cuh)
+static_assert(sizeof(DbgHitH) == 56 && sizeof(rt_debug_scatter_out) == 44, "debug record layouts");
+} // namespace
+
+
+extern "C" {
+
+rt_status rt_debug_scatter(rt_camera* c, int32_t object_index, int32_t n, const rt_debug_hit* hits, const double* uniforms,
+                           rt_debug_scatter_out* out) {
+  RT_GUARD_BEGIN
+  if (!c || n < 0 || (n > 0 && (!hits || !uniforms || !out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  int root = -1;
+  for (const I2& si : c->hs.slot_info)
+    if ((si.y & 0x3fffffff) == object_index) { root = si.x; break; }
+  if (root < 0) return fail(RT_ERR_INVALID_ARGUMENT, "object_index out of range");
+  if (n == 0) return RT_OK;
+  DeviceGuard g(c->device);
+  std::vector<DbgHitH> hh((size_t)n);
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < 3; ++a) {
+      hh[i].ro[a] = (float)hits[i].ray_origin[a]; hh[i].rd[a] = (float)hits[i].ray_dir[a];
+      hh[i].p[a] = (float)hits[i].p[a]; hh[i].n[a] = (float)hits[i].normal[a];
+      hh[i].front = hits[i].front_face; hh[i].pad = 0;
+    }
+  DbgBuf B;
+  DbgHitH* d_h = nullptr; float* d_u = nullptr; rt_debug_scatter_out* d_o = nullptr;
+  CU(B.up(hh, &d_h)); CU(B.up(to_f32(uniforms, (size_t)n * RT_DEBUG_UNIFORMS), &d_u)); CU(B.out((size_t)n, &d_o));
+  CU(launch_debug_scatter(c->ds, root, n, d_h, d_u, d_o, c->stream));
+  CU(cudaMemcpyAsync(out, d_o, (size_t)n * sizeof(*out), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+  RT_GUARD_END
+}
+
+rt_status rt_debug_get_ray(rt_camera* c, int32_t n, const int32_t* ij, const double* uniforms, float* ray_out, int32_t* used) {
+  RT_GUARD_BEGIN
+  if (!c || n < 0 || (n > 0 && (!ij || !uniforms || !ray_out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return RT_OK;
+  DeviceGuard g(c->device);
+  DbgBuf B;
+  int* d_ij = nullptr; float* d_u = nullptr; float* d_o = nullptr; int* d_used = nullptr;
+  CU(B.up(std::vector<int>(ij, ij + 2 * (size_t)n), &d_ij));
+  CU(B.up(to_f32(uniforms, (size_t)n * RT_DEBUG_UNIFORMS), &d_u));
+  CU(B.out((size_t)n * 6, &d_o)); CU(B.out((size_t)n, &d_used));
+  CU(launch_debug_get_ray(c->ds, n, d_ij, d_u, d_o, d_used, c->stream));
+  CU(cudaMemcpyAsync(ray_out, d_o, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (used) CU(cudaMemcpyAsync(used, d_used, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+  RT_GUARD_END
+}
+
+rt_status rt_debug_light_pdf(rt_camera* c, int32_t light, int32_t n, const double* origin, const double* direction, float* value) {
+  RT_GUARD_BEGIN
+  if (!c || n < 0 || (n > 0 && (!origin || !direction || !value))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (light < 0 || light >= (int)c->hs.lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
+  if (n == 0) return RT_OK;
+  DeviceGuard g(c->device);
+  DbgBuf B;
+  float *d_o = nullptr, *d_d = nullptr, *d_v = nullptr;
+  CU(B.up(to_f32(origin, 3 * (size_t)n), &d_o)); CU(B.up(to_f32(direction, 3 * (size_t)n), &d_d)); CU(B.out((size_t)n, &d_v));
+  CU(launch_debug_light_pdf(c->ds, light, n, d_o, d_d, d_v, c->stream));
+  CU(cudaMemcpyAsync(value, d_v, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+  RT_GUARD_END
+}
+
+rt_status rt_debug_light_random_vec(rt_camera* c, int32_t light, int32_t n, const double* origin, const double* uniforms, float* out) {
+  RT_GUARD_BEGIN
+  if (!c || n < 0 || (n > 0 && (!origin || !uniforms || !out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (light < 0 || light >= (int)c->hs.lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
+  if (n == 0) return RT_OK;
+  DeviceGuard g(c->device);
+  DbgBuf B;
+  float *d_o = nullptr, *d_u = nullptr, *d_v = nullptr;
+  CU(B.up(to_f32(origin, 3 * (size_t)n), &d_o)); CU(B.up(to_f32(uniforms, (size_t)n * RT_DEBUG_UNIFORMS), &d_u)); CU(B.out(3 * (size_t)n, &d_v));
+  CU(launch_debug_light_random(c->ds, light, n, d_o, d_u, d_v, c->stream));
+  CU(cudaMemcpyAsync(out, d_v, 3 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+  RT_GUARD_END
+}
+
+rt_status rt_debug_diffuse_bounce(rt_camera* c, int32_t n, const double* p, const double* normal, const double* uniforms, float* out) {
+  RT_GUARD_BEGIN
+  if (!c || n < 0 || (n > 0 && (!p || !normal || !uniforms || !out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (n == 0) return RT_OK;
+  DeviceGuard g(c->device);
+  DbgBuf B;
+  float *d_p = nullptr, *d_n = nullptr, *d_u = nullptr, *d_v = nullptr;
+  CU(B.up(to_f32(p, 3 * (size_t)n), &d_p)); CU(B.up(to_f32(normal, 3 * (size_t)n), &d_n));
+  CU(B.up(to_f32(uniforms, (size_t)n * RT_DEBUG_UNIFORMS), &d_u)); CU(B.out(6 * (size_t)n, &d_v));
+  CU(launch_debug_diffuse(c->ds, n, d_p, d_n, d_u, d_v, c->stream));
+  CU(cudaMemcpyAsync(out, d_v, 6 * (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return RT_OK;
+  RT_GUARD_END
 }
 
 } // extern "C"

@@ -101,21 +101,6 @@ RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, floa
   return slot >= 0;
 }
 
-// MixturePDF([cosine, lights...], [0.5, 0.5/n ...]) constants — camera.ts:287-288, pdf.ts:66-72
-struct MixW {
-  int nl;
-  float wl, total_w, inv_total_w;
-};
-RT_DEV MixW make_mixw(const DevScene& S) {
-  MixW m;
-  m.nl = S.n_lights;
-  m.wl = m.nl > 0 ? 0.5f / (float)m.nl : 0.f;
-  m.total_w = 0.5f;
-  for (int k = 0; k < m.nl; ++k) m.total_w += m.wl; // summed like weights.reduce (pdf.ts:71)
-  m.inv_total_w = 1.0f / m.total_w;
-  return m;
-}
-
 struct PathState {
   Ray ray;
   V3 tp, radiance;
@@ -168,25 +153,10 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
     return false;
   }
   // camera.ts:285-315 with the mixture pdf of pdf.ts:57-99
-  const Onb onb = make_onb<true>(sf.n);
-  const float rnd = g.next() * mw.total_w;
-  const float r1 = g.next(), r2 = g.next();
-  V3 dir = onb_local(onb, cosine_direction(r1, r2));
-  if (mw.nl > 0) {
-    float partial = 0.5f;
-    int chosen = mw.nl - 1;
-    for (int k = 0; k < mw.nl; ++k) {
-      partial += mw.wl;
-      if (rnd < partial) { chosen = k; break; }
-    }
-    V3 ldir = light_random_vec(S.lights[chosen], sf.p, r1, r2);
-    dir = sel3(rnd < 0.5f, dir, ldir);
-  }
-  const float cz = dot3(dir, onb.w); // all three generators return unit vectors
-  const float cosv = cz <= 0.f ? 0.f : cz * 0.31830988618f;
-  float sum = 0.5f * cosv;
-  for (int k = 0; k < mw.nl; ++k) sum = fmaf(mw.wl, light_pdf_value(S, S.lights[k], sf.p, dir), sum);
-  const float pdf_value = sum * mw.inv_total_w;
+  const float u_sel = g.next(), r1 = g.next(), r2 = g.next();
+  V3 dir;
+  float cosv, pdf_value;
+  diffuse_bounce(S, mw, sf.p, sf.n, u_sel, r1, r2, dir, cosv, pdf_value);
   if (!(pdf_value > 0.0001f)) return true; // camera.ts:298-301 (NaN also ends the path)
   ps.tp = ps.tp * (sc.attenuation * (cosv * rcp_approx(pdf_value)));
   ps.ray = Ray{sf.p, dir};
@@ -1383,7 +1353,9 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   static const bool pool_list = getenv("RT_B200_POOL_LIST") != nullptr;   // development switches
   static const bool no_trav = getenv("RT_B200_NO_TRAV") != nullptr;
   static const bool env_sorted = getenv("RT_B200_SORTED") != nullptr;
-  const bool sorted_list = env_sorted || R.sorted;
+  // k_render_sorted ends its CTA loop when no warp holds samples, so it cannot write the pixels of an image with
+  // zero samples per pixel (black image, camera.ts:406); k_render_pool's epilogue runs for every item.
+  const bool sorted_list = (env_sorted || R.sorted) && S.cam.samples > 0;
   switch (S.bvh_kind) {
     case BVH_LIST:
       if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
@@ -1442,3 +1414,4 @@ cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st)
 } // namespace rt
 
 #include "rt_wavefront.cuh" // the wavefront integrator shares every helper above
+#include "rt_debug.cuh"     // per-function parity hooks: the same device functions on explicit inputs

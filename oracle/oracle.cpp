@@ -140,6 +140,9 @@ struct Rng {
   // mode 1
   uint64_t s0 = 1, s1 = 2;
   uint64_t draws = 0;
+  // mode 2: the caller supplies the sequence Math.random() returns (per-function parity hooks); past its end: 0.5
+  const double* list = nullptr;
+  uint64_t list_n = 0;
 
   void seed_sequential(uint64_t sd) {
     // splitmix64 expansion of the seed
@@ -165,6 +168,7 @@ struct Rng {
   }
   double next() {
     ++draws;
+    if (mode == 2) return draws <= list_n ? list[draws - 1] : 0.5;
     if (mode == 0) {
       if (idx % 5u == 0) {
         uint32_t ctr[4] = {idx / 5u, stream, (uint32_t)seed, (uint32_t)(seed >> 32)};
@@ -814,6 +818,40 @@ struct Camera {
     return Ray{origin, dir};
   }
 
+  // The diffuse branch of rayColor (camera.ts:285-308): direction from the mixture pdf, its value, and the
+  // scatter pdf's value for that direction.  One function so that rayColor and the parity hook share it.
+  void diffuseBounce(V3 p, V3 pdfNormal, Rng& g, V3& direction, double& pdfValue, double& spv) const {
+    CosinePDF cpdf(pdfNormal);
+    // MixturePDF([scatterPdf, ...lights], [0.5, 0.5/n ...]) — camera.ts:287-288, pdf.ts:57-99
+    size_t n = lights.size();
+    double totalWeight = 0;
+    totalWeight += 0.5;
+    for (size_t k = 0; k < n; ++k) totalWeight += 0.5 / n;
+    // generate
+    {
+      double rnd = g.next() * totalWeight;
+      double partial = 0.5;
+      int chosen = -1; // -1 = cosine
+      bool found = rnd < partial;
+      if (!found) {
+        for (size_t k = 0; k < n; ++k) {
+          partial += 0.5 / n;
+          if (rnd < partial) { chosen = (int)k; found = true; break; }
+        }
+        if (!found) chosen = n ? (int)n - 1 : -1; // fallback to last PDF
+      }
+      direction = chosen < 0 ? cpdf.generate(g) : lights[chosen]->pdfRandomVec(p, g);
+    }
+    double sum = 0;
+    sum += 0.5 * cpdf.value(direction);
+    for (size_t k = 0; k < n; ++k) {
+      CNT(light_pdf_evals);
+      sum += (0.5 / n) * lights[k]->pdfValue(p, direction);
+    }
+    pdfValue = sum / totalWeight;
+    spv = cpdf.value(direction);
+  }
+
   V3 rayColor(const Ray& r, V3 throughput, int& bounces, Rng& g) const { // camera.ts:221-319
     if (bounces > 0) g.begin_stream((uint32_t)bounces); // stream 0 continues after the camera-ray draws
     if (bounces >= depth) return mk(0, 0, 0);
@@ -843,38 +881,11 @@ struct Camera {
       return add(emitted, sc);
     }
     if (sr.hasPdf) {
-      CosinePDF cpdf(sr.pdfNormal);
-      // MixturePDF([scatterPdf, ...lights], [0.5, 0.5/n ...]) — camera.ts:287-288, pdf.ts:57-99
-      size_t n = lights.size();
-      double totalWeight = 0;
-      totalWeight += 0.5;
-      for (size_t k = 0; k < n; ++k) totalWeight += 0.5 / n;
-      // generate
       V3 direction;
-      {
-        double rnd = g.next() * totalWeight;
-        double partial = 0.5;
-        int chosen = -1; // -1 = cosine
-        bool found = rnd < partial;
-        if (!found) {
-          for (size_t k = 0; k < n; ++k) {
-            partial += 0.5 / n;
-            if (rnd < partial) { chosen = (int)k; found = true; break; }
-          }
-          if (!found) chosen = n ? (int)n - 1 : -1; // fallback to last PDF
-        }
-        direction = chosen < 0 ? cpdf.generate(g) : lights[chosen]->pdfRandomVec(rec.p, g);
-      }
+      double pdfValue, spv;
+      diffuseBounce(rec.p, sr.pdfNormal, g, direction, pdfValue, spv);
       Ray scattered{rec.p, direction};
-      double sum = 0;
-      sum += 0.5 * cpdf.value(direction);
-      for (size_t k = 0; k < n; ++k) {
-        CNT(light_pdf_evals);
-        sum += (0.5 / n) * lights[k]->pdfValue(rec.p, direction);
-      }
-      double pdfValue = sum / totalWeight;
       if (pdfValue <= 0.0001) return emitted;
-      double spv = cpdf.value(direction);
       V3 brdf = scale(sr.attenuation, spv);
       V3 nt = divs(mulv(throughput, brdf), pdfValue);
       V3 inc = rayColor(scattered, nt, bounces, g);
@@ -1346,6 +1357,71 @@ int orc_material_scatter(const rt_scene_desc* s, int root, const double* ro, con
                     sr.hasScattered ? sr.scattered.d.z : 0.0, (double)sr.reflected};
   std::memcpy(out, vals, sizeof(vals));
   return 1;
+}
+
+// ---- per-function hooks with EXPLICIT uniforms: the caller supplies the sequence Math.random() would return,
+// so the CUDA device functions (rt_debug_* in include/rt_b200.h) can be driven with the very same numbers ----
+static Rng listRng(const double* u, int n) { Rng g; g.mode = 2; g.list = u; g.list_n = (uint64_t)(n > 0 ? n : 0); return g; }
+
+// material.scatter + material.emitted at a synthetic hit (materials/*.ts).  out = [scattered?, pdf?, att r,g,b,
+// dir x,y,z, reflected]; returns 1 = scattered / pdf result, 0 = null (absorbed / light), < 0 = bad scene.
+int orc_material_scatter_u(const rt_scene_desc* s, int root, const double* ro, const double* rd, const double* p, const double* n,
+                           int frontFace, const double* uniforms, int n_uniforms, double* out, float* emitted, int* used) {
+  std::vector<std::unique_ptr<Material>> pool;
+  rt_status st = RT_OK;
+  Material* m = buildMaterial(*s, root, pool, st);
+  if (!m) return -(int)st;
+  HitRecord rec{mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), 1.0, frontFace != 0, m, 0};
+  Rng g = listRng(uniforms, n_uniforms);
+  ScatterResult sr;
+  bool ok = m->scatter(Ray{mk(ro[0], ro[1], ro[2]), mk(rd[0], rd[1], rd[2])}, rec, g, sr);
+  V3 e = m->emitted(rec);
+  if (emitted) { emitted[0] = e.x; emitted[1] = e.y; emitted[2] = e.z; }
+  if (used) *used = (int)g.draws;
+  if (!ok) return 0;
+  double vals[9] = {(double)sr.hasScattered, (double)sr.hasPdf, sr.attenuation.x, sr.attenuation.y, sr.attenuation.z,
+                    sr.hasScattered ? sr.scattered.d.x : 0.0, sr.hasScattered ? sr.scattered.d.y : 0.0,
+                    sr.hasScattered ? sr.scattered.d.z : 0.0, (double)sr.reflected};
+  std::memcpy(out, vals, sizeof(vals));
+  return 1;
+}
+// Camera.getRay(i, j) (camera.ts:176-210)
+int orc_get_ray_u(void* cam, int i, int j, const double* uniforms, int n_uniforms, float* origin, float* dir, int* used) {
+  Camera* c = (Camera*)cam;
+  Rng g = listRng(uniforms, n_uniforms);
+  Ray r = c->getRay(i, j, g);
+  origin[0] = r.o.x; origin[1] = r.o.y; origin[2] = r.o.z;
+  dir[0] = r.d.x; dir[1] = r.d.y; dir[2] = r.d.z;
+  if (used) *used = (int)g.draws;
+  return RT_OK;
+}
+// lights[k].pdfValue(origin, direction) of the camera's light list (quad.ts:123-140, sphere.ts:106-131)
+double orc_light_pdf_value(void* cam, int k, const double* o, const double* d) {
+  Camera* c = (Camera*)cam;
+  if (k < 0 || (size_t)k >= c->lights.size()) return -1.0;
+  return c->lights[(size_t)k]->pdfValue(mk(o[0], o[1], o[2]), mk(d[0], d[1], d[2]));
+}
+// lights[k].pdfRandomVec(origin) (quad.ts:148-158, sphere.ts:140-147)
+int orc_light_random_vec_u(void* cam, int k, const double* o, const double* uniforms, int n_uniforms, float* out, int* used) {
+  Camera* c = (Camera*)cam;
+  if (k < 0 || (size_t)k >= c->lights.size()) return RT_ERR_INVALID_ARGUMENT;
+  Rng g = listRng(uniforms, n_uniforms);
+  V3 v = c->lights[(size_t)k]->pdfRandomVec(mk(o[0], o[1], o[2]), g);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z;
+  if (used) *used = (int)g.draws;
+  return RT_OK;
+}
+// The diffuse branch of rayColor (camera.ts:285-308) at a hit point with normal n: out = [dir x,y,z, pdfValue,
+// scatterPdfValue, continues (pdfValue > 0.0001)].
+int orc_diffuse_bounce_u(void* cam, const double* p, const double* n, const double* uniforms, int n_uniforms, double* out, int* used) {
+  Camera* c = (Camera*)cam;
+  Rng g = listRng(uniforms, n_uniforms);
+  V3 dir;
+  double pdfValue, spv;
+  c->diffuseBounce(mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), g, dir, pdfValue, spv);
+  out[0] = dir.x; out[1] = dir.y; out[2] = dir.z; out[3] = pdfValue; out[4] = spv; out[5] = pdfValue <= 0.0001 ? 0.0 : 1.0;
+  if (used) *used = (int)g.draws;
+  return RT_OK;
 }
 
 // finalColor + writeColorToBuffer on one colour (camera.ts:455-472)

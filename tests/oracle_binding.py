@@ -87,6 +87,13 @@ def lib() -> C.CDLL:
         L.orc_mixed_weight_clamp.argtypes = [C.c_double]
         L.orc_mixed_weight_clamp.restype = C.c_double
         L.orc_material_scatter.argtypes = [C.POINTER(rt_scene_desc), C.c_int, dp, dp, dp, dp, C.c_int, C.c_uint64, C.c_uint32, dp, fp]
+        ip = C.POINTER(C.c_int)
+        L.orc_material_scatter_u.argtypes = [C.POINTER(rt_scene_desc), C.c_int, dp, dp, dp, dp, C.c_int, dp, C.c_int, dp, fp, ip]
+        L.orc_get_ray_u.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, C.c_int, fp, fp, ip]
+        L.orc_light_pdf_value.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.orc_light_pdf_value.restype = C.c_double
+        L.orc_light_random_vec_u.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_int, fp, ip]
+        L.orc_diffuse_bounce_u.argtypes = [C.c_void_p, dp, dp, dp, C.c_int, dp, ip]
         L.orc_write_color.argtypes = [dp, C.POINTER(C.c_uint8)]
         L.orc_pixel_converged.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         L.orc_vec3_op.argtypes = [C.c_int, dp, dp, C.c_double, fp]
@@ -195,3 +202,47 @@ class OracleCamera:
         d = (C.c_float * 3)()
         lib().orc_get_ray(self.h, i, j, sample, seed, o, d)
         return np.array(o, dtype=np.float32), np.array(d, dtype=np.float32)
+
+
+# ---- per-function hooks with explicit uniforms (the CPU side of tests/test_gpu_functions.py) ----
+def _dn(v):
+    a = [float(x) for x in v]
+    return (C.c_double * len(a))(*a)
+
+
+def material_scatter_u(flat: FlatScene, root: int, ray_origin, ray_dir, p, normal, front_face, uniforms):
+    """material.scatter + emitted with the given Math.random() sequence.
+    Returns (kind, attenuation, dir, emitted, used, reflected); kind 0 null / 1 scattered ray / 2 pdf."""
+    out = (C.c_double * 9)()
+    em = (C.c_float * 3)()
+    used = C.c_int()
+    rc = lib().orc_material_scatter_u(C.byref(flat.desc), int(root), d3(ray_origin), d3(ray_dir), d3(p), d3(normal), int(bool(front_face)),
+                                      _dn(uniforms), len(uniforms), out, em, C.byref(used))
+    if rc < 0:
+        raise OracleError(f"status {-rc}")
+    o = list(out)
+    kind = 0 if rc == 0 else (1 if o[0] == 1.0 else 2)
+    return kind, np.array(o[2:5]), np.array(o[5:8]), np.array(list(em)), used.value, (bool(o[8]) if rc else False)
+
+
+def get_ray_u(cam: "OracleCamera", i, j, uniforms):
+    o, d, used = (C.c_float * 3)(), (C.c_float * 3)(), C.c_int()
+    lib().orc_get_ray_u(cam.h, int(i), int(j), _dn(uniforms), len(uniforms), o, d, C.byref(used))
+    return np.array(o, np.float32), np.array(d, np.float32), used.value
+
+
+def light_pdf_value(cam: "OracleCamera", k, origin, direction) -> float:
+    return float(lib().orc_light_pdf_value(cam.h, int(k), d3(origin), d3(direction)))
+
+
+def light_random_vec_u(cam: "OracleCamera", k, origin, uniforms):
+    out, used = (C.c_float * 3)(), C.c_int()
+    lib().orc_light_random_vec_u(cam.h, int(k), d3(origin), _dn(uniforms), len(uniforms), out, C.byref(used))
+    return np.array(out, np.float32), used.value
+
+
+def diffuse_bounce_u(cam: "OracleCamera", p, normal, uniforms):
+    """[dir x,y,z, mixture pdf value, scatter pdf value, continues], uniforms used"""
+    out, used = (C.c_double * 6)(), C.c_int()
+    lib().orc_diffuse_bounce_u(cam.h, d3(p), d3(normal), _dn(uniforms), len(uniforms), out, C.byref(used))
+    return np.array(list(out)), used.value

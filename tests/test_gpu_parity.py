@@ -393,6 +393,23 @@ def test_zero_samples_gives_black_image(gpu):  # while (pixel.samples < 0) never
     assert not g["rgb8"].any()
 
 
+@pytest.mark.parametrize("integrator", ["auto", "sorted", "megakernel", "wavefront"])
+@pytest.mark.parametrize("name", ["C5-layered", "C1-spheres"])
+def test_zero_samples_every_integrator(gpu, name, integrator, monkeypatch):
+    """AUTO picks the sorted kernel for Mixed/Layered scenes; an image with no samples is black there too, every pixel is
+    written and counted (stale device memory of a recycled buffer must not leak out), also with more chunks than samples."""
+    sd = SCENES[name]()
+    gpu_render(sd, {"width": 64, "samples": 8, "aTolerance": 0, "integrator": integrator})  # leaves a non-black image in the cache
+    g = gpu_render(sd, {"width": 64, "samples": 0, "integrator": integrator})
+    H, W = g["rgb8"].shape[:2]
+    assert g["stats"].pixels == W * H and g["stats"].samples["total"] == 0 and not g["rgb8"].any()
+    monkeypatch.setenv("RT_B200_CHUNKS", "16")
+    a = gpu_render(sd, {"width": 64, "samples": 3, "aTolerance": 0, "integrator": integrator})
+    monkeypatch.delenv("RT_B200_CHUNKS")
+    b = gpu_render(sd, {"width": 64, "samples": 3, "aTolerance": 0, "integrator": integrator})
+    assert a["stats"].pixels == W * H and np.array_equal(a["rgb8"], b["rgb8"])
+
+
 def test_render_modes(gpu):  # camera.ts:326-340
     sd = SCENES["C1-spheres"]()
     base = {"width": 96, "samples": 40, "aTolerance": 0.05, "seed": 2}
