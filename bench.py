@@ -259,7 +259,7 @@ def main():
     import torch.distributed as dist
 
     from mcp_raytracer_b200 import _native, createCameraFromSceneData, measureFp32Peak
-    from mcp_raytracer_b200.distributed import gather_framebuffer, merge_stats
+    from mcp_raytracer_b200.distributed import SharedFramebuffer, gather_owned_blocks, merge_stats
     from mcp_raytracer_b200.scene_data import rt_stats
 
     if not torch.cuda.is_available() or _native.lib().rt_device_count() < 1:
@@ -280,7 +280,17 @@ def main():
     W, H = cam.imageWidth, cam.imageHeight
     stream = torch.cuda.current_stream()
     cam.setStream(stream.cuda_stream)
-    fb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+    # N > 1: ONE framebuffer, in rank 0's memory, that every rank's render kernel writes its own blocks into (CUDA IPC +
+    # NVLink peer stores); if the ranks cannot map it, each rank renders into its own buffer and rank 0 gathers the owned
+    # pixels (1/N of the image per rank) with one NCCL gather.
+    shared = SharedFramebuffer(W, H, local_rank) if world > 1 else None
+    peer_writes = bool(shared and shared.ok)
+    if peer_writes:
+        fb_ptr = shared.ptr
+        fb = shared.as_tensor() if rank == 0 else None
+    else:
+        fb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
+        fb_ptr = fb.data_ptr()
     stats_dev = torch.zeros(64, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_fb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
@@ -293,7 +303,7 @@ def main():
         return rt_stats.from_buffer_copy(raw)
 
     def step_device():
-        cam.renderRegionDevice(None, fb.data_ptr(), 0, 0, stats_dev.data_ptr())
+        cam.renderRegionDevice(None, fb_ptr, 0, 0, stats_dev.data_ptr())
 
     # warm-up (untimed)
     for _ in range(max(args.warmup, 3) if args.warmup >= 3 else args.warmup):
@@ -322,8 +332,18 @@ def main():
     sums = torch.tensor([st_local.pixels, st_local.samples_total, st_local.bounces_total, st_local.rays], dtype=torch.int64, device=dev)
     mins = torch.tensor([st_local.samples_min, st_local.bounces_min], dtype=torch.int64, device=dev)
     maxs = torch.tensor([st_local.samples_max, st_local.bounces_max], dtype=torch.int64, device=dev)
+    rank_ms = [local_ms / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        rank_ms = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    rank_paths = [int(st_local.samples_total)]
+    if world > 1:
+        mine = torch.tensor([int(st_local.samples_total)], dtype=torch.int64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        rank_paths = [int(x.item()) for x in every]
     merge_stats(sums, mins, maxs)
     total_ms = float(t.item())
     paths_per_step, rays_per_step = int(sums[1].item()), int(sums[3].item())
@@ -333,32 +353,51 @@ def main():
     #      render + gather + D2H ----
     from mcp_raytracer_b200.scene_data import FlatScene
 
-    def e2e_step():
-        c = createCameraFromSceneData(sd, {**ropts, **part})
+    phases = {"create": 0.0, "render": 0.0, "exchange": 0.0, "d2h": 0.0, "destroy": 0.0}
+
+    def e2e_step(record):
+        t0 = time.perf_counter()
+        c = createCameraFromSceneData(sd, {**ropts, **part})       # SceneData flatten + scene compile (BVH build) + H2D upload
         c.setStream(stream.cuda_stream)
+        t1 = time.perf_counter()
         if world > 1:
-            fb.zero_()
-            c.renderRegionDevice(None, fb.data_ptr(), 0, 0, stats_dev.data_ptr())
-            gather_framebuffer(fb)
+            c.renderRegionDevice(None, fb_ptr, 0, 0, stats_dev.data_ptr())
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if peer_writes:
+                dist.barrier()                                     # every rank's pixels are in rank 0's framebuffer
+            else:
+                gather_owned_blocks(fb)
+                torch.cuda.synchronize()
+            t3 = time.perf_counter()
             if rank == 0:
                 host_fb.copy_(fb, non_blocking=True)
+                stats_dev.cpu()
             torch.cuda.synchronize()
+            t4 = time.perf_counter()
         else:
-            c.render(host_fb.numpy().reshape(-1))
+            c.render(host_fb.numpy().reshape(-1))                  # render + D2H of the RGB8 image and the stats, synchronous
+            t2 = t3 = t4 = time.perf_counter()
         c.close()
+        t5 = time.perf_counter()
+        if record:
+            for k, v in zip(phases, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                phases[k] += 1e3 * v / args.steps
 
     for _ in range(2):
-        e2e_step()
+        e2e_step(False)
     barrier()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_step()
+        e2e_step(True)
     barrier()
     e2e_s = time.perf_counter() - e0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
+    import hashlib
+    fb_sha1 = hashlib.sha1(host_fb.numpy().tobytes()).hexdigest() if rank == 0 else None   # identical for every N
     fs = FlatScene(sd)
     h2d = int(sum(a.nbytes for a in (fs.obj_type, fs.obj_pos, fs.obj_u, fs.obj_v, fs.obj_r, fs.obj_material, fs.obj_light,
                                      fs.mat_type_a, fs.mat_color_a, fs.mat_param_a, fs.mat_child_a)))
@@ -366,6 +405,9 @@ def main():
 
     if rank != 0:
         cam.close()
+        if shared:
+            dist.barrier()
+            shared.close()
         if world > 1:
             dist.destroy_process_group()
         return 0
@@ -410,19 +452,26 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": label + (" [OVERRIDDEN size: development run]" if overridden else ""), "image": f"{W}x{H}", "spp": ropts["samples"],
                    "bvh": {1: "reference", 2: "sah", 3: "list"}.get(cam.info.bvh_kind), "integrator": {1: "megakernel", 2: "wavefront", 3: "sorted"}.get(cam.info.integrator_kind),
-                   "partition": f"16x16 tiles, owner=(tx+ty)%{world}", "rng": "Philox4x32-10 keyed (pixel,sample), counter (block,bounce)",
+                   "partition": f"8x4 pixel blocks, one per rank per run of {world} blocks, order rotated by a hash of the run (rt_block_owner)",
+                   "exchange": ("none (1 GPU)" if world == 1 else "render kernels store owned pixels into rank 0's framebuffer over NVLink (CUDA IPC peer mapping); no collective"
+                                if peer_writes else "NCCL gather of each rank's owned pixels (1/N of the image)"), "rng": "Philox4x32-10 keyed (pixel,sample), counter (block,bounce)",
                    "l2": "256 MiB memset between steps, outside the per-step CUDA-event pairs"},
         "grays_per_s": grays, "paths_per_step": paths_per_step, "rays_per_step": rays_per_step,
         "wall_s_timed_region": wall, "step_ms": step_ms,
+        "rank_ms": {"min": min(rank_ms), "median": statistics.median(rank_ms), "max": max(rank_ms), "per_rank": rank_ms},
+        "rank_paths": rank_paths, "fb_sha1": fb_sha1,
         "clocks": {k: clocks[k] for k in ("sm_mhz", "sm_max_mhz", "reasons")} if clocks else None,
         "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": 1e3 * e2e_s / args.steps,
+                "ms_per_step": 1e3 * e2e_s / args.steps, "breakdown_ms": phases,
                 "includes": "SceneData flatten + BVH build + H2D + render + gather + D2H of the RGB8 framebuffer and stats"},
         "gpu_launches": kernel_launches_per_step * args.steps * world,
         "roofline": roof, "cpu_baseline": cpu,
     }
     emit(line)
     cam.close()
+    if shared:
+        dist.barrier()
+        shared.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
   RT_OK = 0,
@@ -132,8 +132,10 @@ typedef struct rt_render_opts {
   int32_t bvh;            /* RT_BVH_* */
   int32_t integrator;     /* RT_INTEGRATOR_* */
   int32_t device;         /* CUDA device ordinal, -1 = current */
-  /* image-space partition for one-process-per-GPU runs: 16x16 tiles, tile k belongs to
-   * part (k + row_shift) % part_count; only owned pixels are rendered/written. */
+  /* image-space partition for one-process-per-GPU runs (and, internally, rt_multi_*): the unit is the 8x4
+   * pixel block; every run of part_count consecutive blocks (row-major over the whole image) gives each part
+   * one block, in an order rotated by a hash of the run's index (block_owner, csrc/rt_types.h; Python mirror
+   * mcp_raytracer_b200/distributed.py).  Only owned pixels are rendered / written. */
   int32_t part_index;     /* 0 <= part_index < part_count */
   int32_t part_count;     /* <= 1 means the whole region */
 } rt_render_opts;
@@ -200,7 +202,8 @@ rt_status rt_camera_render(rt_camera* cam, uint8_t* rgb8, size_t rgb8_len, float
 /* Same as rt_camera_render_region but rgb8 / linear_rgb / moments are DEVICE pointers on
  * the camera's device and nothing is copied or synchronised: the call returns once the
  * kernels are enqueued on the camera's stream.  `moments` (optional, device,
- * [H][W][8] float) receives per pixel: sum r,g,b, sum r^2,g^2,b^2, samples, bounces.
+ * [H][W][8] float) receives per pixel: sum r,g,b; the sum of squared deviations of r,g,b from the
+ * pixel mean (Welford: variance = that / (samples - 1)); samples; bounces.
  * `stats_dev` (optional, device, sizeof(rt_stats)) receives the reduced statistics
  * except device_ms. */
 rt_status rt_camera_render_region_device(rt_camera* cam, const rt_region* region, uint8_t* rgb8_dev,
@@ -218,6 +221,33 @@ rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint
  * t [H][W], normal [H][W][3] (the reference's face-forwarded rec.normal), front_face. */
 rt_status rt_camera_trace_primary(rt_camera* cam, const rt_region* region, int32_t* obj_id,
                                   float* t, float* normal, uint8_t* front_face);
+
+/* ---- one process, N GPUs: replaces the worker pool of generateImageBuffer(parallel: true)
+ *      (src/raytracer.ts:60-90: N worker_threads over row strips of a SharedArrayBuffer, RenderStats.merge) ----
+ * The scene is compiled once and uploaded to `n_devices` GPUs (devices == NULL: ordinals 0..n-1; n_devices <= 0:
+ * every visible GPU).  Device k renders the 8x4 blocks it owns and its kernels store the finished pixels directly
+ * into device[0]'s framebuffer over NVLink peer mappings — no gather step, no collective; where peer access is
+ * not available each device renders into its own buffer and the owned blocks are merged on the host.  The image
+ * is bit-identical to rt_camera_render_region's for every n_devices.  opts->device / part_* are ignored. */
+typedef struct rt_multi rt_multi;
+rt_status rt_multi_create(const rt_scene_desc* scene, const rt_render_opts* opts, int32_t n_devices,
+                          const int32_t* devices, rt_multi** out);
+rt_status rt_multi_destroy(rt_multi* multi);
+/* info (optional): the camera block of device[0]; n_devices / peer_writes (optional): GPUs in use, 1 = the
+ * peer-write path is active. */
+rt_status rt_multi_get_info(const rt_multi* multi, rt_camera_info* info, int32_t* n_devices, int32_t* peer_writes);
+/* Camera.renderRegion over all the GPUs: HOST buffers as rt_camera_render_region; stats merged like
+ * RenderStats.merge (src/render-utils/renderStats.ts:42-64), device_ms = the slowest device.  Synchronous. */
+rt_status rt_multi_render_region(rt_multi* multi, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
+                                 float* linear_rgb, rt_stats* stats);
+
+/* ---- one process PER GPU (torch.distributed ranks of one node): a device buffer every rank can write ----
+ * Rank 0 creates the framebuffer and hands the 64-byte CUDA IPC handle to the other ranks (any transport);
+ * they open it and pass the pointer as rgb8_dev to rt_camera_render_region_device: their kernels then write
+ * the pixels they own straight into rank 0's memory (the SharedArrayBuffer of src/raytracer.ts:71-72). */
+rt_status rt_shared_buffer_create(int32_t device, size_t bytes, void** dev_ptr, uint8_t handle[64]);
+rt_status rt_shared_buffer_open(int32_t device, const uint8_t handle[64], void** dev_ptr);
+rt_status rt_shared_buffer_release(int32_t device, void* dev_ptr, int32_t opened /* 1: from _open, 0: from _create */);
 
 /* ---- per-function parity hooks ----------------------------------------------------------------
  * Each call runs ONE device function of the render path (the same code the render kernels inline) on
@@ -265,6 +295,9 @@ rt_status rt_debug_diffuse_bounce(rt_camera* cam, int32_t n, const double* p, co
 const char* rt_last_error(void);
 int32_t rt_device_count(void);
 int32_t rt_abi_version(void);
+/* which part (0 <= part < part_count) renders pixel (x, y) of an image `image_width` wide: the partition rule of
+ * rt_render_opts.part_index / rt_multi_*, for host code that assembles or checks partitioned renders. */
+int32_t rt_block_owner(int32_t x, int32_t y, int32_t image_width, int32_t part_count);
 /* measured FP32 FMA throughput of `device` in TFLOP/s (dependent-chain FFMA microbenchmark),
  * the roofline denominator for this path. */
 rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_mhz);

@@ -21,7 +21,9 @@ EXPORTS = [
     "rt_camera_create", "rt_camera_destroy", "rt_camera_get_info", "rt_camera_set_stream",
     "rt_camera_render_region", "rt_camera_render", "rt_camera_render_region_device",
     "rt_camera_render_moments", "rt_camera_trace_primary", "rt_last_error", "rt_device_count",
-    "rt_abi_version", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
+    "rt_abi_version", "rt_block_owner", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
+    "rt_multi_create", "rt_multi_destroy", "rt_multi_get_info", "rt_multi_render_region",
+    "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_shared_buffer_release",
     "rt_debug_scatter", "rt_debug_get_ray", "rt_debug_light_pdf", "rt_debug_light_random_vec", "rt_debug_diffuse_bounce",
 ]
 
@@ -59,6 +61,8 @@ def lib() -> C.CDLL:
     L.rt_last_error.restype = C.c_char_p
     L.rt_device_count.restype = C.c_int32
     L.rt_abi_version.restype = C.c_int32
+    L.rt_block_owner.restype = C.c_int32
+    L.rt_block_owner.argtypes = [C.c_int32] * 4
     L.rt_camera_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), C.POINTER(vp)]
     L.rt_camera_destroy.argtypes = [vp]
     L.rt_camera_get_info.argtypes = [vp, C.POINTER(rt_camera_info)]
@@ -72,6 +76,13 @@ def lib() -> C.CDLL:
     L.rt_trim_device_cache.restype = C.c_uint64
     L.rt_scene_validate.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), vp]
     i32 = C.c_int32
+    L.rt_multi_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), i32, vp, C.POINTER(vp)]
+    L.rt_multi_destroy.argtypes = [vp]
+    L.rt_multi_get_info.argtypes = [vp, C.POINTER(rt_camera_info), C.POINTER(i32), C.POINTER(i32)]
+    L.rt_multi_render_region.argtypes = [vp, C.POINTER(rt_region), vp, C.c_size_t, vp, C.POINTER(rt_stats)]
+    L.rt_shared_buffer_create.argtypes = [i32, C.c_size_t, C.POINTER(vp), vp]
+    L.rt_shared_buffer_open.argtypes = [i32, vp, C.POINTER(vp)]
+    L.rt_shared_buffer_release.argtypes = [i32, vp, i32]
     L.rt_debug_scatter.argtypes = [vp, i32, i32, vp, vp, vp]
     L.rt_debug_get_ray.argtypes = [vp, i32, vp, vp, vp, vp]
     L.rt_debug_light_pdf.argtypes = [vp, i32, i32, vp, vp, vp]

@@ -257,6 +257,67 @@ class Camera:
         return out
 
 
+class MultiCamera:
+    """One process, N GPUs (rt_multi_*): the native stand-in for the reference's worker pool (src/raytracer.ts:60-90).
+    Same `render` / `renderRegion` as `Camera`; device k renders the 8x4 blocks it owns and writes them straight into
+    device 0's framebuffer over NVLink peer mappings."""
+
+    channels = 3
+
+    def __init__(self, sceneData: Dict[str, Any], renderData: Optional[Dict[str, Any]] = None, devices: Optional[List[int]] = None,
+                 nDevices: int = 0):
+        self._flat = FlatScene(sceneData)
+        self.options = merge_render_options(sceneData.get("render"), renderData)
+        self._opts = render_opts_struct(self.options)
+        L = _native.lib()
+        h = C.c_void_p()
+        dev = (C.c_int32 * len(devices))(*devices) if devices else None
+        st = L.rt_multi_create(C.byref(self._flat.desc), C.byref(self._opts), len(devices) if devices else int(nDevices), dev, C.byref(h))
+        if st != 0:
+            raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(st, st)}]")
+        self._h = h
+        info, n, p2p = rt_camera_info(), C.c_int32(), C.c_int32()
+        L.rt_multi_get_info(self._h, C.byref(info), C.byref(n), C.byref(p2p))
+        self.info = info
+        self.imageWidth, self.imageHeight = info.image_width, info.image_height
+        self.nDevices, self.peerWrites = n.value, bool(p2p.value)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            _native.lib().rt_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def renderRegion(self, buffer: np.ndarray, region: Optional[Dict[str, int]], linear: Optional[np.ndarray] = None) -> RenderStats:
+        W, H = self.imageWidth, self.imageHeight
+        if buffer is not None and (buffer.dtype != np.uint8 or not buffer.flags["C_CONTIGUOUS"]):
+            raise RaytracerError("pixel buffer must be a C-contiguous uint8 array")
+        if linear is not None and (linear.dtype != np.float32 or linear.size < W * H * 3):
+            raise RaytracerError("linear buffer must be float32 [H][W][3]")
+        reg = _region_struct(region, W, H)
+        st = rt_stats()
+        rc = _native.lib().rt_multi_render_region(self._h, C.byref(reg), buffer.ctypes.data if buffer is not None else None,
+                                                  buffer.nbytes if buffer is not None else 0,
+                                                  linear.ctypes.data if linear is not None else None, C.byref(st))
+        if rc != 0:
+            raise RaytracerError(f"{_native.last_error()} [{_native.STATUS_NAMES.get(rc, rc)}]")
+        return RenderStats.from_struct(st)
+
+    def render(self, pixelData: np.ndarray, linear: Optional[np.ndarray] = None) -> RenderStats:
+        return self.renderRegion(pixelData, None, linear)
+
+
 def createCameraFromSceneData(sceneData: Dict[str, Any], renderOptions: Optional[Dict[str, Any]] = None) -> Camera:
     """src/scenes/scenes.ts:60-104"""
     return Camera(sceneData, None, renderOptions)

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <thread>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -150,12 +152,13 @@ struct DeviceGuard { // switch to the camera's device for the duration of a call
 };
 
 struct rt_camera {
-  HostScene hs;
+  std::shared_ptr<HostScene> hs; // compiled scene; shared by the cameras of an rt_multi (one per GPU)
   DevScene ds{};
   rt_render_opts opts{};
   int device = 0;
   int integrator = RT_INTEGRATOR_MEGAKERNEL;
   cudaStream_t stream = nullptr;
+  bool owns_stream = false; // rt_multi gives each device its own stream
   double build_ms = 0;
   // scene buffers
   std::vector<void*> allocs;
@@ -215,11 +218,12 @@ static void free_camera(rt_camera* c) {
   wf_release(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->owns_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
 
 static rt_status clip_region(const rt_camera* c, const rt_region* r, RenderParams& P) {
-  const int W = c->hs.image_width, H = c->hs.image_height;
+  const int W = c->hs->image_width, H = c->hs->image_height;
   rt_region full{0, 0, W, H};
   if (!r) r = &full;
   if (r->x < 0 || r->y < 0 || r->width < 0 || r->height < 0) return fail(RT_ERR_INVALID_ARGUMENT, "negative region");
@@ -251,6 +255,10 @@ extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
 int32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+int32_t rt_block_owner(int32_t x, int32_t y, int32_t image_width, int32_t part_count) {
+  if (part_count <= 1 || x < 0 || y < 0 || image_width <= 0) return 0;
+  return block_owner(x / 8, y / 4, (image_width + 7) / 8, part_count);
+}
 uint64_t rt_trim_device_cache(void) {
   DevCache& C = dev_cache();
   std::lock_guard<std::mutex> lk(C.mu);
@@ -374,18 +382,14 @@ int32_t rt_device_count(void) {
   return n;
 }
 
-rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opts, rt_camera** out) {
-  if (!scene || !opts || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+// Upload a compiled scene to `opts->device` and make the camera (everything of rt_camera_create after the scene compiler).
+static rt_status camera_from_host(std::shared_ptr<HostScene> hs, const rt_render_opts* opts, rt_camera** out, double compile_ms) {
   *out = nullptr;
   rt_camera* c = nullptr;
   try {
   auto t0 = std::chrono::steady_clock::now();
-  // validate + compile first: scene errors are reported even on a box without a GPU,
-  // exactly like the reference throws before rendering anything
   c = new rt_camera();
-  std::string err;
-  rt_status st = compile_scene(scene, opts, c->hs, err);
-  if (st != RT_OK) { delete c; return fail(st, err); }
+  c->hs = hs;
   if (opts->part_count > 1 && (opts->part_index < 0 || opts->part_index >= opts->part_count)) {
     delete c;
     return fail(RT_ERR_INVALID_ARGUMENT, "part_index out of range");
@@ -396,7 +400,7 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   if (opts->integrator == RT_INTEGRATOR_AUTO) {
     // composite materials (Mixed / Layered) make neighbouring lanes run different shading code: sorting the
     // CTA's hits by material class pays there (+8 % on the 49-sphere layered/mixed scene), not on Cornell (-8 %)
-    for (const I4& m : c->hs.matB)
+    for (const I4& m : c->hs->matB)
       if (m.x == MAT_MIXED || m.x == MAT_LAYERED) { c->integrator = RT_INTEGRATOR_SORTED; break; }
   }
   int ndev = rt_device_count();
@@ -408,30 +412,31 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
   DeviceGuard g(dev);
   if (!g.ok) { delete c; return fail(RT_ERR_CUDA, "cudaSetDevice failed"); }
   DevScene& d = c->ds;
-  d.cam = c->hs.cam;
+  d.cam = c->hs->cam;
   const Node* nodes = nullptr;
 #define UP(vec, ptr)                                   \
   do {                                                 \
     rt_status s_ = upload(c, vec, ptr);                \
     if (s_ != RT_OK) { free_camera(c); return s_; }    \
   } while (0)
-  UP(c->hs.nodes, &nodes);
+  UP(c->hs->nodes, &nodes);
   d.nodes = reinterpret_cast<const F4*>(nodes);
-  UP(c->hs.p0, &d.p0); UP(c->hs.p1, &d.p1); UP(c->hs.p2, &d.p2); UP(c->hs.p3, &d.p3);
-  UP(c->hs.slot_info, &d.slot_info); UP(c->hs.exact, &d.exact);
-  UP(c->hs.matA, &d.matA); UP(c->hs.matB, &d.matB); UP(c->hs.matE, &d.matE);
-  UP(c->hs.lights, &d.lights);
+  UP(c->hs->p0, &d.p0); UP(c->hs->p1, &d.p1); UP(c->hs->p2, &d.p2); UP(c->hs->p3, &d.p3);
+  UP(c->hs->slot_info, &d.slot_info); UP(c->hs->exact, &d.exact);
+  UP(c->hs->matA, &d.matA); UP(c->hs->matB, &d.matB); UP(c->hs->matE, &d.matE);
+  UP(c->hs->lights, &d.lights);
 #undef UP
-  d.n_nodes = (int)c->hs.nodes.size();
-  d.n_slots = (int)c->hs.p0.size();
-  d.n_unbounded = c->hs.n_unbounded;
-  d.n_mats = (int)c->hs.matA.size();
-  d.n_lights = (int)c->hs.lights.size();
-  d.bvh_kind = c->hs.bvh_kind;
-  d.planar_any = c->hs.planar_any;
-  for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs.list_n[k];
-  d.sph_cmax = c->hs.sph_cmax;
-  d.sph_r2max = c->hs.sph_r2max;
+  d.n_nodes = (int)c->hs->nodes.size();
+  d.n_slots = (int)c->hs->p0.size();
+  d.n_unbounded = c->hs->n_unbounded;
+  d.n_mats = (int)c->hs->matA.size();
+  d.n_lights = (int)c->hs->lights.size();
+  d.bvh_kind = c->hs->bvh_kind;
+  d.planar_any = c->hs->planar_any;
+  for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs->list_n[k];
+  d.sph_cmax = c->hs->sph_cmax;
+  d.sph_r2max = c->hs->sph_r2max;
+  for (int k = 0; k < 3; ++k) d.aa_cmax[k] = c->hs->aa_cmax[k];
   d.seed_lo = (uint32_t)opts->seed;
   d.seed_hi = (uint32_t)(opts->seed >> 32);
   if (dev_alloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
@@ -448,13 +453,39 @@ rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opt
       if (v >= 1 && v <= 64) c->chunks = v;
     }
   }
-  c->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->build_ms = compile_ms + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   *out = c;
   return RT_OK;
   } catch (const std::exception& e) { // std::bad_alloc on a huge scene: nothing half-built stays behind
     if (c) free_camera(c);
     return fail(RT_ERR_INVALID_ARGUMENT, std::string("rt_camera_create: ") + e.what());
   }
+}
+
+// validate + compile: scene errors are reported even on a box without a GPU, exactly like the reference throws
+// before rendering anything
+static rt_status compile_shared(const rt_scene_desc* scene, const rt_render_opts* opts, std::shared_ptr<HostScene>& hs, double& ms) {
+  try {
+    auto t0 = std::chrono::steady_clock::now();
+    hs = std::make_shared<HostScene>();
+    std::string err;
+    rt_status st = compile_scene(scene, opts, *hs, err);
+    ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (st != RT_OK) return fail(st, err);
+    return RT_OK;
+  } catch (const std::exception& e) {
+    return fail(RT_ERR_INVALID_ARGUMENT, std::string("scene compiler: ") + e.what());
+  }
+}
+
+rt_status rt_camera_create(const rt_scene_desc* scene, const rt_render_opts* opts, rt_camera** out) {
+  if (!scene || !opts || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  std::shared_ptr<HostScene> hs;
+  double ms = 0;
+  rt_status st = compile_shared(scene, opts, hs, ms);
+  if (st != RT_OK) return st;
+  return camera_from_host(hs, opts, out, ms);
 }
 
 rt_status rt_camera_destroy(rt_camera* cam) {
@@ -465,15 +496,15 @@ rt_status rt_camera_destroy(rt_camera* cam) {
 rt_status rt_camera_get_info(const rt_camera* c, rt_camera_info* o) {
   if (!c || !o) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
   std::memset(o, 0, sizeof(*o));
-  const DevCamera& k = c->hs.cam;
-  o->image_width = c->hs.image_width; o->image_height = c->hs.image_height; o->channels = 3;
-  o->n_objects = c->hs.n_objects; o->n_lights = (int)c->hs.lights.size(); o->n_bvh_nodes = (int)c->hs.nodes.size();
-  o->bvh_kind = c->hs.bvh_kind; o->integrator_kind = c->integrator;
+  const DevCamera& k = c->hs->cam;
+  o->image_width = c->hs->image_width; o->image_height = c->hs->image_height; o->channels = 3;
+  o->n_objects = c->hs->n_objects; o->n_lights = (int)c->hs->lights.size(); o->n_bvh_nodes = (int)c->hs->nodes.size();
+  o->bvh_kind = c->hs->bvh_kind; o->integrator_kind = c->integrator;
   std::memcpy(o->center, k.center, 12); std::memcpy(o->pixel00_loc, k.p00, 12);
   std::memcpy(o->pixel_delta_u, k.du, 12); std::memcpy(o->pixel_delta_v, k.dv, 12);
-  std::memcpy(o->u, c->hs.cam_u, 12); std::memcpy(o->v, c->hs.cam_v, 12); std::memcpy(o->w, c->hs.cam_w, 12);
+  std::memcpy(o->u, c->hs->cam_u, 12); std::memcpy(o->v, c->hs->cam_v, 12); std::memcpy(o->w, c->hs->cam_w, 12);
   std::memcpy(o->defocus_disk_u, k.ddu, 12); std::memcpy(o->defocus_disk_v, k.ddv, 12);
-  o->focus_distance = c->hs.focus_distance;
+  o->focus_distance = c->hs->focus_distance;
   o->use_adaptive_sampling = k.adaptive;
   o->device = c->device;
   o->build_ms = c->build_ms;
@@ -499,8 +530,7 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
   owned.reserve((size_t)blocks_x * blocks_y);
   for (int by = 0; by < blocks_y; ++by)
     for (int bx = 0; bx < blocks_x; ++bx) {
-      const int tx = (P.x0 / 16) + (bx >> 1), ty = (P.y0 / 16) + (by >> 2);
-      if (P.part_count > 1 && ((tx + ty) % P.part_count) != P.part_index) continue;
+      if (P.part_count > 1 && block_owner((P.x0 / 16) * 2 + bx, (P.y0 / 16) * 4 + by, (c->hs->image_width + 7) / 8, P.part_count) != P.part_index) continue;
       const int px0 = (P.x0 / 16) * 16 + bx * 8, py0 = (P.y0 / 16) * 16 + by * 4;
       if (px0 >= P.x1 || py0 >= P.y1 || px0 + 8 <= P.x0 || py0 + 4 <= P.y0) continue;
       owned.push_back(by * blocks_x + bx);
@@ -545,7 +575,7 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
   if (!owned.empty()) CU(cudaMemcpy(H.owned_blocks, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice));
   H.n_owned = (int)owned.size();
   H.blocks_x = blocks_x;
-  H.W.total_pairs = (unsigned long long)owned.size() * 32ull * (unsigned long long)std::max(0, c->hs.cam.samples);
+  H.W.total_pairs = (unsigned long long)owned.size() * 32ull * (unsigned long long)std::max(0, c->hs->cam.samples);
   return RT_OK;
 }
 
@@ -557,7 +587,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
   if (P.x1 > P.x0 && P.y1 > P.y0) {
     render_tile_grid(P, &P.tiles_x, &P.tiles_y);
     if (render_needs_full(c->ds, P)) P.chunks = 1;
-    else if (c->chunks > 0) P.chunks = std::min(c->chunks, std::max(1, c->hs.cam.samples)); // never an empty chunk (k_render_sorted skips them)
+    else if (c->chunks > 0) P.chunks = std::min(c->chunks, std::max(1, c->hs->cam.samples)); // never an empty chunk (k_render_sorted skips them)
     else {
       // Sample chunks per pixel: enough (8x4 block, chunk) warp items that the blocks this GPU owns
       // keep it busy for >= 16 rounds of resident warps, so the tail of the render stays ~1/32 of it
@@ -566,10 +596,10 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       const long long owned = std::max(1LL, (long long)P.tiles_x * P.tiles_y * 8 / std::max(1, P.part_count));
       const long long target = 16LL * c->sms * 2 * 8;
       long long k = (target + owned - 1) / owned;
-      k = std::min<long long>(k, std::max(1, c->hs.cam.samples / 16));
+      k = std::min<long long>(k, std::max(1, c->hs->cam.samples / 16));
       P.chunks = (int)std::min<long long>(std::max<long long>(k, 1), 64);
     }
-    if (P.chunks > 1 || !render_needs_full(c->ds, P)) P.chunks = std::max(P.chunks, (c->hs.cam.samples + 2047) / 2048);
+    if (P.chunks > 1 || !render_needs_full(c->ds, P)) P.chunks = std::max(P.chunks, (c->hs->cam.samples + 2047) / 2048);
     const size_t need_q = 1 + (size_t)P.tiles_x * P.tiles_y * 8; // queue head + one completion counter per 8x4 block
     if (need_q > c->queue_ints) {
       CU(cudaStreamSynchronize(c->stream));
@@ -580,7 +610,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     }
     // fixed-point radiance sums [H][W][4] u64, only when a pixel's samples are split over CTAs
     const bool wavefront = c->integrator == RT_INTEGRATOR_WAVEFRONT && !render_needs_full(c->ds, P);
-    const size_t need_s = (P.chunks > 1 || wavefront) ? (size_t)4 * c->hs.image_width * c->hs.image_height : 0;
+    const size_t need_s = (P.chunks > 1 || wavefront) ? (size_t)4 * c->hs->image_width * c->hs->image_height : 0;
     if (need_s > c->scratch_elems) {
       CU(cudaStreamSynchronize(c->stream));
       dev_free(c->d_scratch);
@@ -591,7 +621,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
     CU(cudaMemsetAsync(c->d_queue, 0, need_q * sizeof(int), c->stream));
     if (need_s) {
       // only the rows of the region are touched
-      const size_t row = (size_t)4 * c->hs.image_width;
+      const size_t row = (size_t)4 * c->hs->image_width;
       CU(cudaMemsetAsync(c->d_scratch + row * P.y0, 0, row * (size_t)(P.y1 - P.y0) * sizeof(unsigned long long), c->stream));
     }
     {
@@ -640,7 +670,7 @@ static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb
                              float* moments, rt_stats* stats) {
   RT_GUARD_BEGIN
   if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
-  const int W = c->hs.image_width, H = c->hs.image_height;
+  const int W = c->hs->image_width, H = c->hs->image_height;
   const size_t npx = (size_t)W * H;
   if (rgb8 && rgb8_len < npx * 3) return fail(RT_ERR_BUFFER_TOO_SMALL, "rgb8 buffer smaller than width*height*3");
   DeviceGuard g(c->device);
@@ -679,12 +709,12 @@ static rt_status render_host(rt_camera* c, const rt_region* region, uint8_t* rgb
       if (linear) { hl.resize((size_t)rh * W * 3); CU(cudaMemcpyAsync(hl.data(), c->d_linear + row0 * 3, hl.size() * 4, cudaMemcpyDeviceToHost, c->stream)); }
       if (moments) { hm.resize((size_t)rh * W * 8); CU(cudaMemcpyAsync(hm.data(), c->d_moments + row0 * 8, hm.size() * 4, cudaMemcpyDeviceToHost, c->stream)); }
       CU(cudaStreamSynchronize(c->stream));
+      const int bpr = (W + 7) / 8;
       for (int y = P.y0; y < P.y1; ++y) {
-        const int ty = y / 16;
         for (int x = P.x0; x < P.x1;) {
-          const int tx = x / 16;
-          const int xe = std::min(P.x1, (tx + 1) * 16);
-          if ((tx + ty) % c->opts.part_count == c->opts.part_index) {
+          const int bx = x / 8;
+          const int xe = std::min(P.x1, (bx + 1) * 8);
+          if (block_owner(bx, y / 4, bpr, c->opts.part_count) == c->opts.part_index) {
             const size_t dst = (size_t)y * W + x, src = (size_t)(y - P.y0) * W + x;
             const size_t n = (size_t)(xe - x);
             if (rgb8) std::memcpy(rgb8 + dst * 3, hr.data() + src * 3, n * 3);
@@ -726,7 +756,7 @@ rt_status rt_camera_trace_primary(rt_camera* c, const rt_region* region, int32_t
                                   uint8_t* front_face) {
   if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
   DeviceGuard g(c->device);
-  const int W = c->hs.image_width, H = c->hs.image_height;
+  const int W = c->hs->image_width, H = c->hs->image_height;
   const size_t npx = (size_t)W * H;
   RenderParams P;
   rt_status st = clip_region(c, region, P);
@@ -787,6 +817,251 @@ rt_status rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_clock_
 } // extern "C"
 
 // ---------------------------------------------------------------------------------------------
+// rt_multi: ONE process drives N GPUs — the native replacement of the reference's worker pool
+// (src/raytracer.ts:60-90: N worker_threads, row strips, SharedArrayBuffer).  The scene is compiled once
+// and uploaded to every device; device k renders the 8x4 blocks it owns (block_owner, rt_types.h) and
+// its kernels store the finished pixels STRAIGHT INTO device 0's framebuffer over NVLink peer mappings
+// (3 bytes per pixel, written once): there is no gather step, no staging copy and no collective —
+// device 0's stream waits on one event per peer and copies the image to the caller's buffer.
+// Without peer access between the devices every camera renders into its own buffer and the owned
+// blocks are merged on the host (render_host's partition path), one host thread per device.
+// ---------------------------------------------------------------------------------------------
+struct rt_multi {
+  std::vector<rt_camera*> cams; // part k on devices[k]
+  std::vector<int> devices;
+  bool p2p = false;
+  uint8_t* d_rgb8 = nullptr;    // on devices[0]
+  float* d_linear = nullptr;
+  std::vector<cudaEvent_t> done;
+  unsigned long long* h_stats = nullptr; // pinned [n][kStatCount]
+};
+
+static void free_multi(rt_multi* m) {
+  if (!m) return;
+  for (rt_camera* c : m->cams) free_camera(c);
+  if (!m->devices.empty()) {
+    DeviceGuard g(m->devices[0]);
+    dev_free(m->d_rgb8);
+    dev_free(m->d_linear);
+  }
+  for (size_t k = 0; k < m->done.size(); ++k)
+    if (m->done[k]) { DeviceGuard g(m->devices[k]); cudaEventDestroy(m->done[k]); }
+  if (m->h_stats) cudaFreeHost(m->h_stats);
+  delete m;
+}
+
+extern "C" {
+
+rt_status rt_multi_create(const rt_scene_desc* scene, const rt_render_opts* opts, int32_t n_devices, const int32_t* devices, rt_multi** out) {
+  if (!scene || !opts || !out) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  rt_multi* m = nullptr;
+  try {
+    std::shared_ptr<HostScene> hs;
+    double ms = 0;
+    rt_status st = compile_shared(scene, opts, hs, ms); // scene errors first, like the reference, GPU or not
+    if (st != RT_OK) return st;
+    const int ndev = rt_device_count();
+    if (ndev <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+    if (n_devices <= 0) n_devices = ndev;
+    m = new rt_multi();
+    for (int k = 0; k < n_devices; ++k) {
+      const int d = devices ? devices[k] : k;
+      if (d < 0 || d >= ndev) { free_multi(m); return fail(RT_ERR_INVALID_ARGUMENT, "device ordinal out of range"); }
+      for (int prev : m->devices)
+        if (prev == d) { free_multi(m); return fail(RT_ERR_INVALID_ARGUMENT, "device listed twice"); }
+      m->devices.push_back(d);
+    }
+    // every device must be able to write device[0]'s memory, else the host-merge path is used
+    m->p2p = true;
+    for (int k = 1; k < n_devices && m->p2p; ++k) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, m->devices[k], m->devices[0]) != cudaSuccess || !can) { cudaGetLastError(); m->p2p = false; break; }
+      DeviceGuard g(m->devices[k]);
+      const cudaError_t e = cudaDeviceEnablePeerAccess(m->devices[0], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) m->p2p = false;
+      cudaGetLastError();
+    }
+    if (getenv("RT_B200_MULTI_NO_P2P")) m->p2p = false; // development switch: exercise the host-merge path
+    for (int k = 0; k < n_devices; ++k) {
+      rt_render_opts o = *opts;
+      o.device = m->devices[k];
+      o.part_index = k;
+      o.part_count = n_devices;
+      rt_camera* c = nullptr;
+      st = camera_from_host(hs, &o, &c, k == 0 ? ms : 0.0);
+      if (st != RT_OK) { free_multi(m); return st; }
+      m->cams.push_back(c);
+      DeviceGuard g(m->devices[k]);
+      cudaEvent_t ev = nullptr;
+      // each device renders on its own non-blocking stream: the legacy default stream would serialise them
+      if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+        const std::string msg = cudaGetErrorString(cudaGetLastError());
+        free_multi(m);
+        return fail(RT_ERR_CUDA, "rt_multi_create: stream/event: " + msg);
+      }
+      c->owns_stream = true;
+      m->done.push_back(ev);
+    }
+    if (cudaMallocHost(&m->h_stats, sizeof(unsigned long long) * kStatCount * (size_t)n_devices) != cudaSuccess) {
+      cudaGetLastError();
+      free_multi(m);
+      return fail(RT_ERR_CUDA, "rt_multi_create: pinned stats buffer");
+    }
+    *out = m;
+    return RT_OK;
+  } catch (const std::exception& e) {
+    if (m) free_multi(m);
+    return fail(RT_ERR_INVALID_ARGUMENT, std::string("rt_multi_create: ") + e.what());
+  }
+}
+
+rt_status rt_multi_destroy(rt_multi* m) {
+  free_multi(m);
+  return RT_OK;
+}
+
+rt_status rt_multi_get_info(const rt_multi* m, rt_camera_info* info, int32_t* n_devices, int32_t* peer_writes) {
+  if (!m || m->cams.empty()) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (n_devices) *n_devices = (int32_t)m->cams.size();
+  if (peer_writes) *peer_writes = m->p2p ? 1 : 0;
+  return info ? rt_camera_get_info(m->cams[0], info) : RT_OK;
+}
+
+rt_status rt_multi_render_region(rt_multi* m, const rt_region* region, uint8_t* rgb8, size_t rgb8_len, float* linear, rt_stats* stats) {
+  RT_GUARD_BEGIN
+  if (!m || m->cams.empty()) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  const int n = (int)m->cams.size();
+  rt_camera* c0 = m->cams[0];
+  const int W = c0->hs->image_width, H = c0->hs->image_height;
+  const size_t npx = (size_t)W * H;
+  if (rgb8 && rgb8_len < npx * 3) return fail(RT_ERR_BUFFER_TOO_SMALL, "rgb8 buffer smaller than width*height*3");
+  if (stats) std::memset(stats, 0, sizeof(*stats));
+  if (!m->p2p && n > 1) {
+    // host merge: one thread per device, each copies the blocks it owns into the caller's buffer
+    std::vector<rt_status> st((size_t)n, RT_OK);
+    std::vector<std::string> msg((size_t)n);
+    std::vector<rt_stats> ps((size_t)n);
+    std::vector<std::thread> th;
+    for (int k = 0; k < n; ++k)
+      th.emplace_back([&, k]() {
+        st[k] = render_host(m->cams[k], region, rgb8, rgb8_len, linear, nullptr, &ps[k]);
+        if (st[k] != RT_OK) msg[k] = g_err;
+      });
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n; ++k)
+      if (st[k] != RT_OK) return fail(st[k], msg[k]);
+    if (stats) {
+      stats->samples_min = stats->bounces_min = 0x7fffffff;
+      for (const rt_stats& s : ps) {
+        stats->pixels += s.pixels; stats->samples_total += s.samples_total; stats->bounces_total += s.bounces_total; stats->rays += s.rays;
+        stats->samples_min = std::min(stats->samples_min, s.samples_min); stats->samples_max = std::max(stats->samples_max, s.samples_max);
+        stats->bounces_min = std::min(stats->bounces_min, s.bounces_min); stats->bounces_max = std::max(stats->bounces_max, s.bounces_max);
+        stats->device_ms = std::max(stats->device_ms, s.device_ms); stats->kernel_launches += s.kernel_launches;
+      }
+    }
+    return RT_OK;
+  }
+  // ---- peer-write path ----
+  {
+    DeviceGuard g0(m->devices[0]);
+    if (rgb8 && !m->d_rgb8) CU(dev_alloc(&m->d_rgb8, npx * 3));
+    if (linear && !m->d_linear) CU(dev_alloc(&m->d_linear, npx * 3 * sizeof(float)));
+  }
+  RenderParams P0;
+  int launches_total = 0;
+  for (int k = 0; k < n; ++k) {
+    rt_camera* c = m->cams[k];
+    DeviceGuard g(c->device);
+    RenderParams P;
+    rt_status st = clip_region(c, region, P);
+    if (st != RT_OK) return st;
+    P.rgb8 = rgb8 ? m->d_rgb8 : nullptr;       // device 0's framebuffer, peer-mapped on device k
+    P.linear = linear ? m->d_linear : nullptr;
+    int launches = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    st = enqueue_render(c, P, nullptr, &launches);
+    if (st != RT_OK) return st;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    CU(cudaMemcpyAsync(m->h_stats + (size_t)k * kStatCount, c->d_stats, sizeof(unsigned long long) * kStatCount, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(m->done[k], c->stream));
+    launches_total += launches;
+    if (k == 0) P0 = P;
+  }
+  {
+    DeviceGuard g0(m->devices[0]);
+    for (int k = 1; k < n; ++k) CU(cudaStreamWaitEvent(c0->stream, m->done[k], 0)); // peers' pixels have landed in device 0's memory
+    const int rw = P0.x1 - P0.x0, rh = P0.y1 - P0.y0;
+    if (rw > 0 && rh > 0) {
+      const size_t off = (size_t)P0.y0 * W + P0.x0;
+      if (rgb8) CU(cudaMemcpy2DAsync(rgb8 + off * 3, (size_t)W * 3, m->d_rgb8 + off * 3, (size_t)W * 3, (size_t)rw * 3, rh, cudaMemcpyDeviceToHost, c0->stream));
+      if (linear) CU(cudaMemcpy2DAsync(linear + off * 3, (size_t)W * 12, m->d_linear + off * 3, (size_t)W * 12, (size_t)rw * 12, rh, cudaMemcpyDeviceToHost, c0->stream));
+    }
+    CU(cudaStreamSynchronize(c0->stream));
+  }
+  if (stats) {
+    unsigned long long raw[kStatCount];
+    std::memcpy(raw, kStatsInit, sizeof(raw));
+    double ms_max = 0;
+    for (int k = 0; k < n; ++k) {
+      const unsigned long long* r = m->h_stats + (size_t)k * kStatCount;
+      raw[kStatPixels] += r[kStatPixels]; raw[kStatSamples] += r[kStatSamples]; raw[kStatBounces] += r[kStatBounces]; raw[kStatRays] += r[kStatRays];
+      raw[kStatSamplesMin] = std::min(raw[kStatSamplesMin], r[kStatSamplesMin]); raw[kStatSamplesMax] = std::max(raw[kStatSamplesMax], r[kStatSamplesMax]);
+      raw[kStatBouncesMin] = std::min(raw[kStatBouncesMin], r[kStatBouncesMin]); raw[kStatBouncesMax] = std::max(raw[kStatBouncesMax], r[kStatBouncesMax]);
+      DeviceGuard g(m->cams[k]->device);
+      float ms = 0;
+      CU(cudaEventElapsedTime(&ms, m->cams[k]->ev0, m->cams[k]->ev1));
+      ms_max = std::max(ms_max, (double)ms);
+    }
+    unpack_stats(raw, stats);
+    stats->device_ms = ms_max; // the slowest device (they run concurrently)
+    stats->kernel_launches = launches_total;
+  }
+  return RT_OK;
+  RT_GUARD_END
+}
+
+// ---- framebuffer shared between the one-process-per-GPU ranks of a node (CUDA IPC) ----
+rt_status rt_shared_buffer_create(int32_t device, size_t bytes, void** dev_ptr, uint8_t handle[64]) {
+  if (!dev_ptr || !handle || bytes == 0) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device visible");
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  DeviceGuard g(device);
+  void* p = nullptr;
+  CU(cudaMalloc(&p, bytes)); // a plain allocation of its own: IPC handles name whole allocations
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return fail(RT_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+  std::memcpy(handle, &h, 64);
+  *dev_ptr = p;
+  return RT_OK;
+}
+rt_status rt_shared_buffer_open(int32_t device, const uint8_t handle[64], void** dev_ptr) {
+  if (!dev_ptr || !handle) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
+  if (rt_device_count() <= 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device visible");
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  DeviceGuard g(device);
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  void* p = nullptr;
+  const cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RT_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+  *dev_ptr = p;
+  return RT_OK;
+}
+rt_status rt_shared_buffer_release(int32_t device, void* dev_ptr, int32_t opened) {
+  if (!dev_ptr) return RT_OK;
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  DeviceGuard g(device);
+  const cudaError_t e = opened ? cudaIpcCloseMemHandle(dev_ptr) : cudaFree(dev_ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); return fail(RT_ERR_CUDA, std::string("rt_shared_buffer_release: ") + cudaGetErrorString(e)); }
+  return RT_OK;
+}
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------
 // per-function parity hooks: stage the records (rounded to FP32 where `Vec3.create` would round them,
 // src/geometry/vec3.ts:263), run one thread per record, copy the answers back.  Synchronous.
 // ---------------------------------------------------------------------------------------------
@@ -825,7 +1100,7 @@ rt_status rt_debug_scatter(rt_camera* c, int32_t object_index, int32_t n, const 
   RT_GUARD_BEGIN
   if (!c || n < 0 || (n > 0 && (!hits || !uniforms || !out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
   int root = -1;
-  for (const I2& si : c->hs.slot_info)
+  for (const I2& si : c->hs->slot_info)
     if ((si.y & 0x3fffffff) == object_index) { root = si.x; break; }
   if (root < 0) return fail(RT_ERR_INVALID_ARGUMENT, "object_index out of range");
   if (n == 0) return RT_OK;
@@ -868,7 +1143,7 @@ rt_status rt_debug_get_ray(rt_camera* c, int32_t n, const int32_t* ij, const dou
 rt_status rt_debug_light_pdf(rt_camera* c, int32_t light, int32_t n, const double* origin, const double* direction, float* value) {
   RT_GUARD_BEGIN
   if (!c || n < 0 || (n > 0 && (!origin || !direction || !value))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
-  if (light < 0 || light >= (int)c->hs.lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
+  if (light < 0 || light >= (int)c->hs->lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
   if (n == 0) return RT_OK;
   DeviceGuard g(c->device);
   DbgBuf B;
@@ -884,7 +1159,7 @@ rt_status rt_debug_light_pdf(rt_camera* c, int32_t light, int32_t n, const doubl
 rt_status rt_debug_light_random_vec(rt_camera* c, int32_t light, int32_t n, const double* origin, const double* uniforms, float* out) {
   RT_GUARD_BEGIN
   if (!c || n < 0 || (n > 0 && (!origin || !uniforms || !out))) return fail(RT_ERR_INVALID_ARGUMENT, "null argument");
-  if (light < 0 || light >= (int)c->hs.lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
+  if (light < 0 || light >= (int)c->hs->lights.size()) return fail(RT_ERR_INVALID_ARGUMENT, "light_index out of range");
   if (n == 0) return RT_OK;
   DeviceGuard g(c->device);
   DbgBuf B;

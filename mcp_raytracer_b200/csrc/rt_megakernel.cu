@@ -36,6 +36,21 @@ static constexpr int kListMax = 128;
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 2
 #endif
+// CTA geometry of k_render_pool<LIST> (warp-persistent: the CTA only shares the staged scene, so its size is free):
+// threads x resident CTAs decides the register cap (65536 / (threads x CTAs), granularity 8) and the warps per SM.
+#ifndef RT_LIST_THREADS
+#define RT_LIST_THREADS 256
+#endif
+#ifndef RT_LIST_BLOCKS
+#define RT_LIST_BLOCKS 3
+#endif
+// ... and of k_render_trav (deep trees: latency-bound on node fetches, so warps per SM matter more than spill-free registers)
+#ifndef RT_TRAV_THREADS
+#define RT_TRAV_THREADS 256
+#endif
+#ifndef RT_TRAV_BLOCKS
+#define RT_TRAV_BLOCKS RT_MIN_BLOCKS
+#endif
 #ifndef RT_TRAV_MIN_LANES
 #define RT_TRAV_MIN_LANES 20 // leave the traversal phase when this many lanes or fewer still traverse
 #endif
@@ -232,7 +247,7 @@ struct WarpItem {
   int blk, px0, py0, s_begin, s_end;
 };
 // Pops items until one belongs to this GPU and touches the region.  False = queue exhausted.
-RT_DEV bool next_warp_item(const RenderParams& R, int samples, unsigned lane, WarpItem& it) {
+RT_DEV bool next_warp_item(const RenderParams& R, int samples, int blocks_per_row, unsigned lane, WarpItem& it) {
   const int chunks = R.chunks;
   const int blocks_x = R.tiles_x * 2, blocks_y = R.tiles_y * 4; // 8x4 blocks covering the tile grid
   const int n_items = blocks_x * blocks_y * chunks;
@@ -243,8 +258,8 @@ RT_DEV bool next_warp_item(const RenderParams& R, int samples, unsigned lane, Wa
     if (item >= n_items) return false;
     const int blk = item / chunks, chunk = item - blk * chunks;
     const int bx = blk % blocks_x, by = blk / blocks_x;
-    const int tx = (R.x0 / kTile) + (bx >> 1), ty = (R.y0 / kTile) + (by >> 2);
-    if (R.part_count > 1 && ((tx + ty) % R.part_count) != R.part_index) continue; // another GPU's tile
+    if (R.part_count > 1 && block_owner((R.x0 / kTile) * 2 + bx, (R.y0 / kTile) * 4 + by, blocks_per_row, R.part_count) != R.part_index)
+      continue; // another GPU's block
     it.px0 = (R.x0 / kTile) * kTile + bx * 8;
     it.py0 = (R.y0 / kTile) * kTile + by * 4;
     if (it.px0 >= R.x1 || it.py0 >= R.y1 || it.px0 + 8 <= R.x0 || it.py0 + 4 <= R.y0) continue; // block outside the region
@@ -328,9 +343,10 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
 // Register budget: the LIST kernel runs 3 CTAs/SM (<= 80 registers, a few spilled words): measured +3 %
 // over 2 CTAs/SM on Cornell; tree kernels keep 2 (their traversal stacks live in local memory already).
 template <int KIND, bool POOL>
-__global__ void __launch_bounds__(256, KIND == BVH_LIST ? 3 : RT_MIN_BLOCKS) k_render_pool(const DevScene S, const RenderParams R) {
+__global__ void __launch_bounds__(KIND == BVH_LIST ? RT_LIST_THREADS : 256, KIND == BVH_LIST ? RT_LIST_BLOCKS : RT_MIN_BLOCKS)
+k_render_pool(const DevScene S, const RenderParams R) {
   __shared__ ListSmem sm;
-  __shared__ unsigned int s_acc[POOL ? 8 : 1][32 * 9];
+  __shared__ unsigned int s_acc[POOL ? (KIND == BVH_LIST ? RT_LIST_THREADS : 256) / 32 : 1][32 * 9];
   const SmemList L = stage_list<KIND>(S, sm);
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? 3 : RT_MIN_BLOCKS) k_r
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
   WarpItem it;
-  while (next_warp_item(R, cam.samples, lane, it)) {
+  while (next_warp_item(R, cam.samples, (cam.width + 7) >> 3, lane, it)) {
     const int pool = 32 * (it.s_end - it.s_begin); // (pixel, sample) pairs of this item
     if (POOL) acc_clear(acc, lane);
 
@@ -381,20 +397,25 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? 3 : RT_MIN_BLOCKS) k_r
         else { sample = next++; fresh = true; have = true; }
       }
       if (__all_sync(0xffffffffu, retired)) break;
+      bool ended = false;
       if (have) {
         const uint32_t pixel = (uint32_t)pi_y * (uint32_t)cam.width + (uint32_t)pi_x;
         if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
         g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
-        if (path_step<KIND>(S, L, sm, mw, ps, g, st_rays)) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
-          if (POOL) acc_add(acc, lp, ps.radiance);
-          else { own[0] += to_fixed(ps.radiance.x); own[1] += to_fixed(ps.radiance.y); own[2] += to_fixed(ps.radiance.z); }
-          ++st_paths;
-          st_bounces += (unsigned)ps.bounces;
-          st_bmin = min(st_bmin, ps.bounces);
-          st_bmax = max(st_bmax, ps.bounces);
-          have = false;
-        }
+        ended = path_step<KIND>(S, L, sm, mw, ps, g, st_rays);
+      }
+#ifdef RT_RECONVERGE
+      __syncwarp(); // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
+#endif
+      if (ended) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
+        if (POOL) acc_add(acc, lp, ps.radiance);
+        else { own[0] += to_fixed(ps.radiance.x); own[1] += to_fixed(ps.radiance.y); own[2] += to_fixed(ps.radiance.z); }
+        ++st_paths;
+        st_bounces += (unsigned)ps.bounces;
+        st_bmin = min(st_bmin, ps.bounces);
+        st_bmax = max(st_bmax, ps.bounces);
+        have = false;
       }
     }
     __syncwarp();
@@ -456,7 +477,7 @@ __global__ void __launch_bounds__(256, 3) k_render_sorted(const DevScene S, cons
     // ---- CTA item = the eight warp items popped by the eight warps ----
     {
       WarpItem it{0, 0, 0, 0, 0};
-      const bool got = next_warp_item(R, cam.samples, lane, it);
+      const bool got = next_warp_item(R, cam.samples, (cam.width + 7) >> 3, lane, it);
       if (lane == 0) {
         ss.it_px0[warp] = it.px0; ss.it_py0[warp] = it.py0; ss.it_blk[warp] = it.blk;
         ss.it_sb[warp] = got ? it.s_begin : 0; ss.it_se[warp] = got ? it.s_end : 0;
@@ -647,7 +668,7 @@ __global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, con
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
   WarpItem it;
-  while (next_warp_item(R, cam.samples, lane, it)) {
+  while (next_warp_item(R, cam.samples, (cam.width + 7) >> 3, lane, it)) {
     const int pool = 32 * (it.s_end - it.s_begin); // (pixel, sample) pairs of this item
     acc_clear(W.acc, lane);
     int next = 0; // warp-uniform cursor into the pairs
@@ -794,8 +815,8 @@ __global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, con
 // =========================================================================================
 enum : int { ST_NONE = 0, ST_BEGIN = 1, ST_TRACE = 2, ST_HIT = 3 };
 
-__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevScene S, const RenderParams R) {
-  __shared__ unsigned int s_acc[8][32 * 9];
+__global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav(const DevScene S, const RenderParams R) {
+  __shared__ unsigned int s_acc[RT_TRAV_THREADS / 32][32 * 9];
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lane = threadIdx.x & 31u;
@@ -807,7 +828,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
   WarpItem it;
-  while (next_warp_item(R, cam.samples, lane, it)) {
+  while (next_warp_item(R, cam.samples, (cam.width + 7) >> 3, lane, it)) {
     const int pool = 32 * (it.s_end - it.s_begin);
     acc_clear(acc, lane);
 
@@ -914,6 +935,18 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_trav(const DevSce
 // spheres 3037 -> 1925 ms, 480 spheres 497 -> 416 ms, layered/mixed 500 -> 483 ms, Cornell 157 -> 170 ms
 // (its cheap all-black pixels now share warps with the expensive ones).
 // =========================================================================================
+// Per-pixel second moment for the parity tests: sum of squared deviations from the running mean (Welford), so a
+// pixel whose samples differ in the 4th digit only (sky gradient under pixel jitter) still gets its variance —
+// sum(c^2) - n mean^2 in FP32 cancels to noise there.  `color` already holds the new sample; n = samples so far.
+RT_DEV void moments_add(V3 color, V3 x, int n, float& m2x, float& m2y, float& m2z) {
+  if (n < 2) return;
+  const float ip = 1.0f / (float)(n - 1), in = 1.0f / (float)n;
+  const V3 mean_old = (color - x) * ip, mean_new = color * in;
+  m2x = fmaf(x.x - mean_old.x, x.x - mean_new.x, m2x);
+  m2y = fmaf(x.y - mean_old.y, x.y - mean_new.y, m2y);
+  m2z = fmaf(x.z - mean_old.z, x.z - mean_new.z, m2z);
+}
+
 // Out of line on purpose: these run once per pixel / per 64 pixels, and the sample loop of k_render_stream is
 // instruction-cache bound like every kernel here (measured: with them inlined the Cornell loop is 13 % slower).
 __device__ __noinline__ void stream_write_pixel(uint8_t* rgb8, float* linear, float* moments, int width, int mode, int depth, int max_samples,
@@ -949,7 +982,7 @@ struct StreamTake {
 };
 __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int blk_x0, int blk_y0, bool queue_empty, int* queue,
                                                int n_items, int tiles_x, int rx0, int ry0, int rx1, int ry1, int part_index, int part_count,
-                                               unsigned lane) {
+                                               int blocks_per_row, unsigned lane) {
   StreamTake tk{0, 0, 0, cursor, blk_x0, blk_y0, queue_empty ? 1 : 0};
   const unsigned lt_mask = (1u << lane) - 1u, full = 0xffffffffu;
   bool mine = (want >> lane) & 1u;
@@ -964,7 +997,7 @@ __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int bl
         if (item >= n_items) { tk.queue_empty = 1; break; }
         const int tile = item >> 3, sub = item & 7;
         const int tx = (rx0 / kTile) + tile % tiles_x, ty = (ry0 / kTile) + tile / tiles_x;
-        if (part_count > 1 && ((tx + ty) % part_count) != part_index) continue; // another GPU's tile
+        if (part_count > 1 && block_owner(tx * 2 + (sub & 1), ty * 4 + (sub >> 1), blocks_per_row, part_count) != part_index) continue; // another GPU's block
         const int bx = tx * kTile + (sub & 1) * 8, by = ty * kTile + (sub >> 1) * 4;
         if (bx >= rx1 || by >= ry1 || bx + 8 <= rx0 || by + 4 <= ry0) continue;
         tk.blk_x0 = bx; tk.blk_y0 = by; tk.cursor = 0;
@@ -1027,7 +1060,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
     const unsigned want = __ballot_sync(full, !have_px);
     if (want != 0u) {
       const StreamTake tk = stream_take(want, cursor, blk_x0, blk_y0, queue_empty, R.queue, n_items, R.tiles_x, R.x0, R.y0, R.x1,
-                                        R.y1, R.part_index, R.part_count, lane);
+                                        R.y1, R.part_index, R.part_count, (cam.width + 7) >> 3, lane);
       cursor = tk.cursor; blk_x0 = tk.blk_x0; blk_y0 = tk.blk_y0; queue_empty = tk.queue_empty != 0;
       if (tk.got) {
         i = tk.i; j = tk.j;
@@ -1063,11 +1096,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
           b_ill += il;
           b_ill2 = fmaf(il, il, b_ill2);
         }
-        if (R.moments) {
-          m2x = fmaf(ps.radiance.x, ps.radiance.x, m2x);
-          m2y = fmaf(ps.radiance.y, ps.radiance.y, m2y);
-          m2z = fmaf(ps.radiance.z, ps.radiance.z, m2z);
-        }
+        if (R.moments) moments_add(color, ps.radiance, samples, m2x, m2y, m2z);
         need_path = true;
         // while (pixel.samples < samples && !pixelConverged(pixel)) — camera.ts:406, evaluated for the next sample
         stop = samples >= cam.samples;
@@ -1148,11 +1177,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
       b_ill += il;
       b_ill2 = fmaf(il, il, b_ill2);
     }
-    if (R.moments) {
-      m2x = fmaf(ps.radiance.x, ps.radiance.x, m2x);
-      m2y = fmaf(ps.radiance.y, ps.radiance.y, m2y);
-      m2z = fmaf(ps.radiance.z, ps.radiance.z, m2z);
-    }
+    if (R.moments) moments_add(color, ps.radiance, samples, m2x, m2y, m2z);
     bool stop = samples >= cam.samples;
     bool check = false;
     if (cam.adaptive && --countdown == 0) {
@@ -1178,7 +1203,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
     const unsigned want = __ballot_sync(full, st == ST_NONE && !have_px);
     if (want != 0u) {
       const StreamTake tk = stream_take(want, cursor, blk_x0, blk_y0, queue_empty, R.queue, n_items, R.tiles_x, R.x0, R.y0, R.x1,
-                                        R.y1, R.part_index, R.part_count, lane);
+                                        R.y1, R.part_index, R.part_count, (cam.width + 7) >> 3, lane);
       cursor = tk.cursor; blk_x0 = tk.blk_x0; blk_y0 = tk.blk_y0; queue_empty = tk.queue_empty != 0;
       if (tk.got) {
         i = tk.i; j = tk.j;
@@ -1296,16 +1321,19 @@ bool render_needs_full(const DevScene& S, const RenderParams& R) {
   return force || S.cam.adaptive || S.cam.mode != 0 || R.moments != nullptr;
 }
 
+// ctas_of_work counts 256-thread CTAs (eight warp items each); kernels with another CTA size scale it.
 template <class K>
-static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderParams& R, long long ctas_of_work, int sms, cudaStream_t st) {
+static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderParams& R, long long ctas_of_work, int sms, cudaStream_t st,
+                                     int threads = 256) {
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
+  ctas_of_work = ctas_of_work * 256 / threads;
   long long resident = (long long)sms * per_sm;
   int grid = (int)(ctas_of_work < resident ? ctas_of_work : resident);
   if (grid < 1) grid = 1;
-  kernel<<<grid, 256, 0, st>>>(S, R);
+  kernel<<<grid, threads, 0, st>>>(S, R);
   return cudaGetLastError();
 }
 
@@ -1358,7 +1386,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   const bool sorted_list = (env_sorted || R.sorted) && S.cam.samples > 0;
   switch (S.bvh_kind) {
     case BVH_LIST:
-      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st);
+      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st, RT_LIST_THREADS);
 #ifdef RT_EXPERIMENTAL_WQ
       {
         static const int wq = getenv("RT_B200_WQ") ? atoi(getenv("RT_B200_WQ")) : 0;
@@ -1374,7 +1402,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
         if (carve != cudaSuccess) return carve;
         return launch_persistent(k_render_sorted<BVH_LIST>, S, R, work, sms, st);
       }
-      return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st);
+      return launch_persistent(k_render_pool<BVH_LIST, false>, S, R, work, sms, st, RT_LIST_THREADS);
     case BVH_SAH:
       // Whole-query while-while walk (k_render_pool) vs traversal bursts interleaved with shading (k_render_trav),
       // rain scene at 1 k ... 100 k spheres with the 4-wide tree (scripts/gpu_trav_threshold.py; n_nodes counts
@@ -1387,7 +1415,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       }
       static const bool trav_always = getenv("RT_B200_TRAV_ALWAYS") != nullptr;
       if (!trav_always && (no_trav || S.n_nodes < kTravNodes)) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
-      return launch_persistent(k_render_trav, S, R, work, sms, st);
+      return launch_persistent(k_render_trav, S, R, work, sms, st, RT_TRAV_THREADS);
     default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);
   }
 }

@@ -110,13 +110,28 @@ struct DevScene {
   int planar_any; // scene has planes/quads
   int list_n[6];  // LIST: slots per kind, in slot order: spheres, axis-aligned quads x/y/z, general quads, planes
   float sph_cmax, sph_r2max; // LIST: max |centre component| and max r^2 over the spheres
+  float aa_cmax[3];          // LIST: max |plane coordinate| of the axis-aligned quads with normal along x / y / z
   uint32_t seed_lo, seed_hi;
 };
+
+// Image partition across GPUs (one process per GPU, or rt_multi_* inside one process).  The unit is the 8x4 pixel
+// block — one warp work item.  Blocks are numbered row-major over the WHOLE image (bx = x / 8, by = y / 4,
+// blocks_per_row = ceil(width / 8)); every run of `n` consecutive blocks gives each part exactly one block, in an
+// order rotated by a hash of the run's index.  Parts are therefore balanced to one block per run (64x4 pixels at
+// n = 8) whatever the image content — no diagonal, row or column structure that could alias with the scene, as the
+// round-1 rule owner = (tile_x + tile_y) % n had — and ownership does not depend on the render region.
+RT_HD inline int block_owner(int bx, int by, int blocks_per_row, int n) {
+  const unsigned i = (unsigned)by * (unsigned)blocks_per_row + (unsigned)bx;
+  const unsigned g = i / (unsigned)n, r = i - g * (unsigned)n;
+  unsigned h = g * 0x9E3779B1u;
+  h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+  return (int)((r + h) % (unsigned)n);
+}
 
 // Per-render launch parameters.
 struct RenderParams {
   int x0, y0, x1, y1;          // region, clipped to the image
-  int part_index, part_count;  // diagonal 16x16 tile interleave; owner = (tx + ty) % part_count
+  int part_index, part_count;  // this GPU renders the 8x4 blocks with block_owner(...) == part_index
   uint8_t* rgb8;               // [H][W][3] or null
   float* linear;               // [H][W][3] or null
   float* moments;              // [H][W][8] or null

@@ -299,8 +299,7 @@ __global__ void __launch_bounds__(256) k_wf_resolve(const DevScene S, const Rend
   bool on = idx < w * h;
   if (on) {
     const int i = R.x0 + idx % w, j = R.y0 + idx / w;
-    const int tx = i / kTile, ty = j / kTile;
-    on = R.part_count <= 1 || ((tx + ty) % R.part_count) == R.part_index;
+    on = R.part_count <= 1 || block_owner(i >> 3, j >> 2, (cam.width + 7) >> 3, R.part_count) == R.part_index;
     if (on) {
       const size_t pi = (size_t)j * cam.width + i;
       const unsigned long long* a = R.accum + pi * 4;

@@ -4,9 +4,10 @@ by native dispatch (the seam SURVEY.md §8b names).
 * `generateImageBuffer(sceneConfig, options)`  <- src/raytracer.ts:39-113
     options.parallel=False : `camera.render(pixelData)`            (raytracer.ts:56-59)
     options.parallel=True  : the image is split over GPUs instead of worker threads
-                             (raytracer.ts:60-90): one Camera per visible device, each renders
-                             its interleaved 16x16-tile set into the shared buffer, stats merged
-                             with RenderStats.merge — the roles `divideIntoRegions` + workers +
+                             (raytracer.ts:60-90): `MultiCamera` (rt_multi_* of the C ABI) compiles
+                             the scene once, every visible device renders its interleaved set of 8x4
+                             blocks and stores them straight into device 0's framebuffer, stats merged
+                             like RenderStats.merge — the roles `divideIntoRegions` + workers +
                              SharedArrayBuffer play in the reference.
   Returns PNG bytes like the reference (PIL instead of sharp; PNG encoding is outside the
   hot path) or, with `options.raw=True`, the RGB8 array itself.
@@ -18,13 +19,12 @@ from __future__ import annotations
 import io
 import math
 import sys
-import threading
 from typing import Any, Dict, List, Optional
 
 import numpy as np
 
 from . import _native
-from .camera import Camera, RenderStats, createCameraFromSceneData
+from .camera import Camera, MultiCamera, RenderStats, createCameraFromSceneData
 from .scenes import generateSceneData
 
 
@@ -58,29 +58,12 @@ def renderScene(sceneConfig: Dict[str, Any], options: Optional[Dict[str, Any]] =
         threads = min(threads, max(ndev, 1))
         if verbose:
             print(f"Starting parallel render on {threads} GPUs", file=sys.stderr)
-        cams = [createCameraFromSceneData(sceneData, {**(render or {}), "device": d, "partIndex": d, "partCount": threads})
-                for d in range(threads)]
-        W, H = cams[0].imageWidth, cams[0].imageHeight
-        pixelData = np.zeros(W * H * 3, np.uint8)  # the SharedArrayBuffer of raytracer.ts:71-72
-        results: List[Optional[RenderStats]] = [None] * threads
-        errors: List[BaseException] = []
-
-        def work(k: int) -> None:
-            try:
-                results[k] = cams[k].render(pixelData)  # disjoint tiles, no locks (renderWorker.ts:23-26)
-            except BaseException as e:  # noqa: BLE001
-                errors.append(e)
-
-        ts = [threading.Thread(target=work, args=(k,)) for k in range(threads)]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        for c in cams:
-            c.close()
-        if errors:
-            raise errors[0]
-        stats = RenderStats.merge([r for r in results if r is not None])
+        # one process, `threads` GPUs, inside the C ABI (rt_multi_*): scene compiled once, every device writes the
+        # blocks it owns into device 0's framebuffer, stats merged like RenderStats.merge (raytracer.ts:71-89)
+        with MultiCamera(sceneData, render, nDevices=threads) as camera:
+            W, H = camera.imageWidth, camera.imageHeight
+            pixelData = np.zeros(W * H * 3, np.uint8)  # the SharedArrayBuffer of raytracer.ts:71-72
+            stats = camera.render(pixelData)
     if verbose:
         print(f"Adaptive sampling stats: avg={stats.samples['avg']:.2f}, min={stats.samples['min']}, max={stats.samples['max']}", file=sys.stderr)
         print(f"Ray bounce stats: avg={stats.bounces['avg']:.2f}, min={stats.bounces['min']}, max={stats.bounces['max']}", file=sys.stderr)

@@ -31,13 +31,26 @@ def block_mean(a: np.ndarray, b: int) -> np.ndarray:
 
 
 def compare_converged(g_mean: np.ndarray, g_var: np.ndarray, n_g: int, o_mean: np.ndarray, o_var: np.ndarray, n_o: int) -> Dict[str, Any]:
-    """g_mean / o_mean: [H,W,3] mean radiance of each render; g_var / o_var: per-sample variance of each."""
+    """g_mean / o_mean: [H,W,3] mean radiance of each render; g_var / o_var: per-sample variance of each.
+
+    Pixels whose ORACLE mean is not finite are counted and left out: one NaN sample poisons a pixel in the reference
+    (PixelStats.add sums it, writeColorToBuffer stores NaN as 0 = a black pixel, src/camera.ts:455-472); the device
+    adds such a sample as 0 instead, so those pixels are not comparable by construction."""
     g_mean, g_var, o_mean, o_var = (np.asarray(a, np.float64) for a in (g_mean, g_var, o_mean, o_var))
+    ok = np.isfinite(o_mean).all(axis=-1) & np.isfinite(o_var).all(axis=-1)
+    n_bad = int((~ok).sum())
+    H, W = g_mean.shape[:2]
+    if n_bad:  # neutralise them: difference 0, variance 0 (they are reported, and bounded by check_converged)
+        g_mean, g_var, o_mean, o_var = g_mean.copy(), g_var.copy(), o_mean.copy(), o_var.copy()
+        o_mean[~ok] = g_mean[~ok]
+        o_var[~ok] = 0.0
+        g_var[~ok] = 0.0
     diff = g_mean - o_mean
     sig2 = g_var / n_g + o_var / n_o           # variance of the difference of two independent estimates
     ref_rms = float(np.sqrt(np.mean(o_mean**2)))
     out: Dict[str, Any] = {
-        "n_gpu": n_g, "n_oracle": n_o, "pixels": int(diff.shape[0] * diff.shape[1]), "ref_rms": ref_rms,
+        "n_gpu": n_g, "n_oracle": n_o, "pixels": int(H * W), "oracle_nonfinite_pixels": n_bad,
+        "gpu_nonfinite_pixels": int((~np.isfinite(g_mean).all(axis=-1)).sum()), "ref_rms": ref_rms,
         # RAW relative RMSE of the two images, per pixel, and what pure Monte-Carlo noise predicts for it
         "rel_rmse_raw": float(np.sqrt(np.mean(diff**2))) / ref_rms,
         "rel_rmse_noise_floor": float(np.sqrt(np.mean(sig2))) / ref_rms,
@@ -53,16 +66,20 @@ def compare_converged(g_mean: np.ndarray, g_var: np.ndarray, n_g: int, o_mean: n
             out["rel_rmse_block"][str(b)] = float(np.sqrt(np.mean(block_mean(diff, b) ** 2))) / ref_rms
             out["rel_rmse_block_noise_floor"][str(b)] = float(np.sqrt(np.mean(block_mean(sig2, b)) / (b * b))) / ref_rms
     sigma = np.sqrt(sig2)
-    lit = sigma > 0                           # channels with zero variance in both renders must agree exactly (below)
+    slack = 2e-6 + 1e-5 * np.abs(o_mean)      # FP32 vs FP64-scalar rounding of a colour both sides agree on (no variance)
+    lit = sigma > slack                       # channels whose Monte-Carlo error is above that rounding level
     z = np.zeros_like(diff)
     z[lit] = diff[lit] / sigma[lit]
-    slack = 2e-6 + 1e-5 * np.abs(o_mean)      # FP32 vs FP64-scalar rounding of a colour both sides agree on (no variance)
     out["frac_within_3sigma"] = float(np.mean(np.abs(diff) <= 3.0 * sigma + slack))
     out["frac_within_4sigma"] = float(np.mean(np.abs(diff) <= 4.0 * sigma + slack))
     out["z2_mean"] = float(np.mean(z[lit] ** 2)) if lit.any() else 0.0   # 1.0 for unbiased estimates with honest variances
     out["z_mean"] = float(np.mean(z[lit])) if lit.any() else 0.0         # 0.0 +- 1/sqrt(N)
-    out["zero_variance_channels"] = int((~lit).sum())
-    out["zero_variance_max_abs_diff"] = float(np.abs(diff[~lit]).max()) if (~lit).any() else 0.0
+    out["quiet_channels"] = int((~lit).sum())                            # (near-)zero variance in both renders: must agree to rounding
+    out["quiet_max_abs_diff"] = float(np.abs(diff[~lit]).max()) if (~lit).any() else 0.0
+    out["quiet_max_excess"] = float((np.abs(diff[~lit]) - 4.0 * sigma[~lit] - slack[~lit]).max()) if (~lit).any() else 0.0
+    worst = np.argsort(-np.abs(z), axis=None)[:8]
+    out["worst_z"] = [{"y": int(i // (W * 3)), "x": int(i // 3 % W), "c": int(i % 3), "gpu": float(g_mean.flat[i]), "oracle": float(o_mean.flat[i]),
+                       "sigma": float(sigma.flat[i]), "z": float(z.flat[i])} for i in worst]
     return out
 
 
@@ -76,7 +93,8 @@ def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002) -> None
     * the 1 % bar: raw relative RMSE <= 1 % on the 8x8 and 16x16 box-filtered images (per-pixel noise at
       ~1000 spp is 1-4 % in EITHER implementation, so a per-pixel 1 % is not a statement about parity; averaging
       64 pixels divides noise by 8 and leaves any bias in place);
-    * whole-image mean radiance within 0.5 % per channel."""
+    * whole-image mean radiance within 0.5 % per channel;
+    * channels without Monte-Carlo variance (flat background, unlit pixels) agree to FP32 rounding."""
     assert r["frac_within_3sigma"] >= 0.9973 - firefly_allowance, r
     assert r["frac_within_4sigma"] >= 0.9995, r
     assert r["rel_rmse_raw"] <= 1.10 * r["rel_rmse_noise_floor"] + 1e-6, r
@@ -86,7 +104,10 @@ def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002) -> None
             assert r["rel_rmse_block"][b] <= 0.01, r
     for a, b in zip(r["mean_gpu"], r["mean_oracle"]):
         assert abs(a - b) <= 0.005 * abs(b) + 1e-6, r
-    assert r["zero_variance_max_abs_diff"] <= 1e-5 * max(1.0, r["ref_rms"]), r
+    assert r["quiet_max_excess"] <= 0.0, r                                # flat-colour channels agree to FP32 rounding
+    assert r["gpu_nonfinite_pixels"] == 0, r
+    # pixels the reference itself would poison with a NaN sample: a handful per billion paths at most
+    assert r["oracle_nonfinite_pixels"] <= max(2, int(2e-5 * r["pixels"])), r
 
 
 def oracle_trace_primary_parallel(oc, threads: int):

@@ -246,7 +246,7 @@ def test_converged_image_rmse_and_3sigma(gpu, name, width, spp):
     gm, om = g["moments"].astype(np.float64), o["moments"]
     n = float(spp)
     g_mean, o_mean = gm[..., 0:3] / n, om[..., 0:3] / n
-    g_var = np.maximum(gm[..., 3:6] / n - g_mean**2, 0) * n / (n - 1)
+    g_var = gm[..., 3:6] / (n - 1)  # the device returns the sum of squared deviations from the mean (rt_b200.h)
     o_var = np.maximum(om[..., 3:6] / n - o_mean**2, 0) * n / (n - 1)
     # 1% relative RMSE of the image, after removing the Monte-Carlo noise both estimates carry
     mse = float(np.mean((g_mean - o_mean) ** 2))
@@ -596,3 +596,83 @@ def test_device_cache_reuse_and_trim(gpu):
     assert trimDeviceCache() > 0
     assert trimDeviceCache() == 0
     assert np.array_equal(first["rgb8"], gpu_render(sd, opts)["rgb8"])
+
+
+# ------------------------------------------------------------------------------------------
+# one process, N GPUs inside the C ABI (rt_multi_*): the worker pool of src/raytracer.ts:60-90
+# ------------------------------------------------------------------------------------------
+def _multi_devices():
+    n = _native.lib().rt_device_count()
+    return [1] + ([n] if n > 1 else [])
+
+
+@pytest.mark.parametrize("name,opts", [("C2-cornell", {"width": 200, "samples": 24}), ("C5-layered", {"width": 120, "samples": 16}),
+                                      ("C3-weekend", {"width": 200, "samples": 8}), ("C1-spheres", {"width": 160, "samples": 40, "aTolerance": 0.05})])
+def test_multi_camera_image_equals_single_camera(gpu, name, opts, monkeypatch):
+    """Every visible GPU (and the 1-GPU degenerate case): same bytes, same merged RenderStats as one Camera, through the
+    peer-write path and through the host-merge fallback, whole image and a ragged region."""
+    from mcp_raytracer_b200 import MultiCamera
+
+    sd = SCENES[name]()
+    opts = {"aTolerance": 0, "seed": 17, **opts}
+    whole = gpu_render(sd, opts)
+    H, W = whole["rgb8"].shape[:2]
+    ws = whole["stats"]
+    for n in _multi_devices():
+        for no_p2p in (False, True):
+            if no_p2p:
+                monkeypatch.setenv("RT_B200_MULTI_NO_P2P", "1")
+            else:
+                monkeypatch.delenv("RT_B200_MULTI_NO_P2P", raising=False)
+            with MultiCamera(sd, opts, nDevices=n) as mc:
+                assert mc.nDevices == n and (mc.imageWidth, mc.imageHeight) == (W, H)
+                assert mc.peerWrites == (not no_p2p) or n == 1 or not mc.peerWrites  # peer access may be unavailable on a box
+                rgb = np.zeros((H, W, 3), np.uint8)
+                lin = np.zeros((H, W, 3), np.float32)
+                st = mc.render(rgb, lin)
+                assert np.array_equal(rgb, whole["rgb8"]) and np.array_equal(lin, whole["linear"]), (n, no_p2p)
+                assert (st.pixels, st.samples, st.bounces["total"], st.bounces["min"], st.bounces["max"], st.rays) == \
+                       (ws.pixels, ws.samples, ws.bounces["total"], ws.bounces["min"], ws.bounces["max"], ws.rays)
+                buf = np.full((H, W, 3), 77, np.uint8)
+                reg = {"x": 9, "y": 6, "width": W // 2 + 3, "height": H // 2 + 1}
+                st = mc.renderRegion(buf, reg)
+                inside = np.zeros((H, W), bool)
+                inside[reg["y"]:reg["y"] + reg["height"], reg["x"]:reg["x"] + reg["width"]] = True
+                assert st.pixels == int(inside.sum())
+                assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], whole["rgb8"][inside])
+    monkeypatch.delenv("RT_B200_MULTI_NO_P2P", raising=False)
+
+
+def test_multi_camera_errors_and_render_scene_parallel(gpu):
+    from mcp_raytracer_b200 import MultiCamera
+
+    sd = SCENES["C2-cornell"]()
+    with pytest.raises(RaytracerError, match="device ordinal out of range"):
+        MultiCamera(sd, {"width": 32}, devices=[0, 99])
+    with pytest.raises(RaytracerError, match="device listed twice"):
+        MultiCamera(sd, {"width": 32}, devices=[0, 0])
+    bad = generateDefaultSceneData()
+    bad["materials"][5]["material"]["outer"] = {"type": "lambert", "color": [1, 1, 1]}
+    with pytest.raises(RaytracerError, match="Material is not a dielectric"):
+        MultiCamera(bad, {"width": 16})
+    # generateImageBuffer(parallel: true) -> all GPUs (raytracer.test.ts:150-173)
+    cfg = {"type": "cornell", "render": {"width": 96, "samples": 8, "aTolerance": 0, "seed": 3}}
+    a, sa = renderScene(cfg)
+    b, sb = renderScene(cfg, {"parallel": True})
+    assert np.array_equal(a, b) and sa.samples == sb.samples and sa.rays == sb.rays
+
+
+def test_partition_blocks_follow_rt_block_owner(gpu):
+    """A part renders exactly the pixels rt_block_owner gives it (the host-side mirror used to assemble images)."""
+    from mcp_raytracer_b200.distributed import tile_owner_mask
+
+    sd = SCENES["C2-cornell"]()
+    opts = {"width": 100, "samples": 2, "aTolerance": 0, "seed": 2}
+    for n, k in ((2, 1), (5, 3), (8, 0)):
+        with createCameraFromSceneData(sd, {**opts, "partIndex": k, "partCount": n}) as cam:
+            buf = np.full((cam.imageHeight, cam.imageWidth, 3), 77, np.uint8)
+            lin = np.full((cam.imageHeight, cam.imageWidth, 3), -1.0, np.float32)
+            st = cam.render(buf, lin)
+            mask = tile_owner_mask(cam.imageWidth, cam.imageHeight, k, n)
+            assert st.pixels == int(mask.sum())
+            assert np.all(lin[~mask] == -1.0) and np.all(lin[mask] >= 0.0)

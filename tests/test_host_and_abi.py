@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = _native.lib()
     for s in declared:
         assert hasattr(lib, s), f"{s} not exported by {_native.LIB_PATH}"
-    assert lib.rt_abi_version() == 1
+    assert lib.rt_abi_version() == 2  # RT_B200_ABI_VERSION (round 2: rt_multi_*, rt_shared_buffer_*, rt_debug_*, rt_block_owner)
     out = subprocess.check_output(["nm", "-D", "--defined-only", _native.LIB_PATH]).decode()
     exported_rt = {l.split()[-1] for l in out.splitlines() if " T rt_" in l}
     assert declared <= exported_rt
@@ -220,6 +220,7 @@ def test_product_package_never_touches_the_oracle():
 
 
 def test_tile_owner_mask_partitions_the_image():
+    from mcp_raytracer_b200 import _native
     from mcp_raytracer_b200.distributed import tile_owner_mask
 
     for W, H, n in ((100, 70, 2), (1024, 1024, 8), (33, 17, 3)):
@@ -228,7 +229,21 @@ def test_tile_owner_mask_partitions_the_image():
             total += tile_owner_mask(W, H, k, n)
         assert np.all(total == 1)
     counts = [tile_owner_mask(1024, 1024, k, 8).sum() for k in range(8)]
-    assert max(counts) - min(counts) <= 0.01 * 1024 * 1024  # balanced
+    assert max(counts) - min(counts) <= 32  # every run of 8 blocks gives each part one: balanced to ONE 8x4 block
+    # each part holds one block of every run of 8: any 64x4 strip aligned to a run is shared by all 8 parts
+    m = np.stack([tile_owner_mask(1024, 1024, k, 8) for k in range(8)])
+    assert np.all(m[:, 0:4, 0:64].reshape(8, -1).sum(axis=1) == 32)
+    # no column or diagonal structure: the owner of block column 0 changes from block row to block row
+    col0 = [int(np.argmax(m[:, y, 0])) for y in range(0, 1024, 4)]
+    assert len(set(col0)) == 8 and max(np.bincount(col0)) < 60
+    # the Python mirror is the C ABI's rule (rt_block_owner = rt::block_owner of the kernels), bit for bit
+    L = _native.lib()
+    rng = np.random.default_rng(0)
+    for W, H, n in ((100, 70, 2), (1000, 700, 8), (33, 17, 3), (3840, 2160, 5)):
+        owner = np.argmax(np.stack([tile_owner_mask(W, H, k, n) for k in range(n)]), axis=0)
+        for _ in range(300):
+            x, y = int(rng.integers(0, W)), int(rng.integers(0, H))
+            assert L.rt_block_owner(x, y, W, n) == owner[y, x]
 
 
 _WORKER = r'''
@@ -246,6 +261,10 @@ t = gather_framebuffer(torch.from_numpy(mine.copy()))
 sums = torch.tensor([int(tile_owner_mask(W, H, rank, world).sum()), 10 * (rank + 1)], dtype=torch.int64)
 mins = torch.tensor([rank + 3], dtype=torch.int64); maxs = torch.tensor([rank + 7], dtype=torch.int64)
 merge_stats(sums, mins, maxs)
+from mcp_raytracer_b200.distributed import SharedFramebuffer
+shared = SharedFramebuffer(W, H, device=0)     # no GPU here: creation fails on rank 0 and EVERY rank learns to fall back
+assert shared.ok is False and shared.ptr == 0
+shared.close()
 if rank == 0:
     assert np.array_equal(t.numpy(), whole), "gathered framebuffer differs"
     assert sums.tolist() == [W * H, 10 * sum(range(1, world + 1))] and mins.item() == 3 and maxs.item() == world + 6
