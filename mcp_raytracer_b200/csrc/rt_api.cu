@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -436,7 +437,6 @@ static rt_status camera_from_host(std::shared_ptr<HostScene> hs, const rt_render
   for (int k = 0; k < 6; ++k) d.list_n[k] = c->hs->list_n[k];
   d.sph_cmax = c->hs->sph_cmax;
   d.sph_r2max = c->hs->sph_r2max;
-  for (int k = 0; k < 3; ++k) d.aa_cmax[k] = c->hs->aa_cmax[k];
   d.seed_lo = (uint32_t)opts->seed;
   d.seed_hi = (uint32_t)(opts->seed >> 32);
   if (dev_alloc(&c->d_stats, sizeof(kStatsInit)) != cudaSuccess || cudaEventCreate(&c->ev0) != cudaSuccess ||
@@ -453,7 +453,9 @@ static rt_status camera_from_host(std::shared_ptr<HostScene> hs, const rt_render
       if (v >= 1 && v <= 64) c->chunks = v;
     }
   }
-  c->build_ms = compile_ms + std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  const double upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  c->build_ms = compile_ms + upload_ms;
+  if (getenv("RT_B200_BUILD_TRACE")) std::fprintf(stderr, "[rt_b200 build] %-12s %8.2f ms (device %d)\n[rt_b200 build] %-12s %8.2f ms\n", "upload", upload_ms, dev, "compile", compile_ms);
   *out = c;
   return RT_OK;
   } catch (const std::exception& e) { // std::bad_alloc on a huge scene: nothing half-built stays behind

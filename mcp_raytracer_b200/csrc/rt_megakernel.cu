@@ -32,7 +32,6 @@
 namespace rt {
 
 static constexpr int kTile = 16;
-static constexpr int kListMax = 128;
 #ifndef RT_MIN_BLOCKS
 #define RT_MIN_BLOCKS 2
 #endif
@@ -78,31 +77,27 @@ RT_DEV void tile_pixel(int idx, int& px, int& py) {
   py = (w >> 1) * 4 + (lane >> 3);
 }
 
-struct ListSmem {
-  F4 p0[kListMax], p1[kListMax], p2[kListMax], p3[kListMax];
-  int type[kListMax];
-  int mat[kListMax];
-};
-
 template <int KIND>
-RT_DEV SmemList stage_list(const DevScene& S, ListSmem& sm) {
-  SmemList L{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+RT_DEV ListSmem stage_list(const DevScene& S, ListSmemData& sm) {
   if (KIND == BVH_LIST) {
     for (int s = threadIdx.x; s < S.n_slots; s += blockDim.x) {
       sm.p0[s] = ldg4(S.p0 + s);
       sm.p1[s] = ldg4(S.p1 + s);
-      sm.p2[s] = ldg4(S.p2 + s);
+      const F4 q2 = ldg4(S.p2 + s);
+      sm.p2[s] = q2;
       sm.p3[s] = ldg4(S.p3 + s);
       I2 info = ldgi2(S.slot_info + s);
       const int ty = (info.y >> 30) & 3;
       // axis-aligned quads get one warp-uniform code per axis so the converged loop never selects components
-      sm.type[s] = ty == OBJ_AAQUAD ? OBJ_AAQUAD + 1 + __float_as_int(sm.p2[s].y) : ty;
+      sm.type[s] = ty == OBJ_AAQUAD ? OBJ_AAQUAD + 1 + __float_as_int(q2.y) : ty;
       sm.mat[s] = info.x;
     }
     __syncthreads();
-    L = SmemList{sm.p0, sm.p1, sm.p2, sm.p3, sm.type, S.n_slots};
   }
-  return L;
+  // the handle is made by a volatile asm placed after the barrier: every ld.shared depends on it, none can move above
+  uint32_t base = KIND == BVH_LIST ? (uint32_t)__cvta_generic_to_shared(&sm) : 0u;
+  asm volatile("mov.u32 %0, %0;" : "+r"(base));
+  return ListSmem{base};
 }
 
 template <int KIND, bool LEAF_LOOP = true> // LEAF_LOOP: see leaves_intersect (rt_device.cuh)
@@ -135,6 +130,7 @@ RT_DEV bool path_pre(const DevCamera& cam, PathState& ps, Rng& g) {
 
 // rayColor, part 2 (camera.ts:249-319) given the closest hit (slot < 0: miss).  True = the path ended
 // (its radiance is complete); otherwise ps.ray / ps.tp / ps.bounces describe the next call.
+#ifndef RT_SINGLE_EXIT
 template <int KIND>
 RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t, int slot) {
   const DevCamera& cam = S.cam;
@@ -147,7 +143,7 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
   }
   int type, root;
   F4 p0;
-  if (KIND == BVH_LIST) { type = sm->type[slot]; root = sm->mat[slot]; p0 = sm->p0[slot]; }
+  if (KIND == BVH_LIST) { type = sm->type(slot); root = sm->mat(slot); p0 = sm->p0(slot); }
   else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
   const Surf sf = surface_at(type, p0, ps.ray, t);
   const I4 mb = ldgi4(S.matB + root);
@@ -177,6 +173,52 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
   ps.ray = Ray{sf.p, dir};
   return false;
 }
+#else
+// Single-exit form: every branch rejoins before the next one starts, so the diffuse and the specular update are
+// laid out once each and the warp reconverges between the stages (miss | emission + dispatch | scatter | update).
+template <int KIND>
+RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t, int slot) {
+  const DevCamera& cam = S.cam;
+  int kind = SCATTER_NONE;
+  V3 att = mk3(0, 0, 0), sdir = mk3(0, 0, 0);
+  Surf sf{mk3(0, 0, 0), mk3(0, 0, 1), true};
+  if (slot < 0) { // camera.ts:252-258
+    V3 ud = normalize3(ps.ray.d);
+    float a = 0.5f * (ud.y + 1.0f);
+    V3 bg = ld3(cam.bg_top) * (1.0f - a) + ld3(cam.bg_bottom) * a;
+    ps.radiance = ps.radiance + bg * ps.tp;
+  } else {
+    int type, root;
+    F4 p0;
+    if (KIND == BVH_LIST) { type = sm->type(slot); root = sm->mat(slot); p0 = sm->p0(slot); }
+    else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
+    sf = surface_at(type, p0, ps.ray, t);
+    const I4 mb = ldgi4(S.matB + root);
+    const F4 ma = ldg4(S.matA + root);
+    if (mb.w) { // emitted * throughput (camera.ts:261)
+      F4 e = ldg4(S.matE + root);
+      ps.radiance = ps.radiance + xyz(e) * ps.tp;
+    }
+    if (mb.x == MAT_LAMBERT) { kind = SCATTER_DIFFUSE; att = xyz(ma); }
+    else if (mb.x != MAT_LIGHT) { // a light: scatter == null, emitted only, bounce not counted (camera.ts:267-269)
+      const Scatter sc = scatter_material(S, root, mb, ma, ps.ray.d, sf, g);
+      kind = sc.kind; att = sc.attenuation; sdir = sc.dir;
+    }
+  }
+  if (kind != SCATTER_NONE) ++ps.bounces; // camera.ts:271
+  if (kind == SCATTER_DIFFUSE) { // camera.ts:285-315 with the mixture pdf of pdf.ts:57-99
+    const float u_sel = g.next(), r1 = g.next(), r2 = g.next();
+    float cosv, pdf_value;
+    diffuse_bounce(S, mw, sf.p, sf.n, u_sel, r1, r2, sdir, cosv, pdf_value);
+    att = att * (cosv * rcp_approx(pdf_value));
+    if (!(pdf_value > 0.0001f)) kind = SCATTER_NONE; // camera.ts:298-301 (NaN also ends the path)
+  }
+  if (kind == SCATTER_NONE) return true;
+  ps.tp = ps.tp * att; // specular: camera.ts:275-282
+  ps.ray = Ray{sf.p, sdir};
+  return false;
+}
+#endif
 
 // One whole rayColor call on the path's current ray.
 template <int KIND, bool LEAF_LOOP = true>
@@ -345,9 +387,10 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
 template <int KIND, bool POOL>
 __global__ void __launch_bounds__(KIND == BVH_LIST ? RT_LIST_THREADS : 256, KIND == BVH_LIST ? RT_LIST_BLOCKS : RT_MIN_BLOCKS)
 k_render_pool(const DevScene S, const RenderParams R) {
-  __shared__ ListSmem sm;
+  __shared__ ListSmemData sm_data;
   __shared__ unsigned int s_acc[POOL ? (KIND == BVH_LIST ? RT_LIST_THREADS : 256) / 32 : 1][32 * 9];
-  const SmemList L = stage_list<KIND>(S, sm);
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lane = threadIdx.x & 31u;
@@ -405,8 +448,10 @@ k_render_pool(const DevScene S, const RenderParams R) {
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
         ended = path_step<KIND>(S, L, sm, mw, ps, g, st_rays);
       }
-#ifdef RT_RECONVERGE
-      __syncwarp(); // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
+#ifndef RT_NO_RECONVERGE
+      // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
+      // instead of one per exit of path_step (measured on Cornell 1024^2 @256: 31.45 -> 30.19 ms)
+      __syncwarp();
 #endif
       if (ended) { // pixel.add(rayColor, bounces) — renderStats.ts:76-88
         if (POOL) acc_add(acc, lp, ps.radiance);
@@ -461,9 +506,10 @@ struct SortSmem {
 
 template <int KIND>
 __global__ void __launch_bounds__(256, 3) k_render_sorted(const DevScene S, const RenderParams R) {
-  __shared__ ListSmem sm;
+  __shared__ ListSmemData sm_data;
   __shared__ SortSmem ss;
-  const SmemList L = stage_list<KIND>(S, sm);
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -511,7 +557,7 @@ __global__ void __launch_bounds__(256, 3) k_render_sorted(const DevScene S, cons
           ++st_rays;
           closest_hit<KIND>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
           if (slot >= 0) {
-            const int root = KIND == BVH_LIST ? sm.mat[slot] : ldgi2(S.slot_info + slot).x;
+            const int root = KIND == BVH_LIST ? sm.mat(slot) : ldgi2(S.slot_info + slot).x;
             type = __ldg(&S.matB[root].x);
           }
         }
@@ -655,10 +701,11 @@ extern __shared__ __align__(16) unsigned char wq_smem[];
 
 template <int KIND, int NS, int BLOCKS>
 __global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, const RenderParams R) {
-  ListSmem& sm = *reinterpret_cast<ListSmem*>(wq_smem);
+  ListSmemData& sm_data = *reinterpret_cast<ListSmemData*>(wq_smem);
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  WqWarp<NS>& W = reinterpret_cast<WqWarp<NS>*>(wq_smem + (KIND == BVH_LIST ? sizeof(ListSmem) : 0))[warp];
-  const SmemList L = stage_list<KIND>(S, sm);
+  WqWarp<NS>& W = reinterpret_cast<WqWarp<NS>*>(wq_smem + (KIND == BVH_LIST ? sizeof(ListSmemData) : 0))[warp];
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -707,7 +754,7 @@ __global__ void __launch_bounds__(256, BLOCKS) k_render_wq(const DevScene S, con
           W.st[1][idx].w = __int_as_float(slot);
           cls = Q_DONE;
           if (slot >= 0) {
-            const int root = KIND == BVH_LIST ? sm.mat[slot] : ldgi2(S.slot_info + slot).x;
+            const int root = KIND == BVH_LIST ? sm.mat(slot) : ldgi2(S.slot_info + slot).x;
             const int type = __ldg(&S.matB[root].x);
             cls = type == MAT_LIGHT ? Q_DONE : type;
           }
@@ -906,11 +953,27 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
           if (__any_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired))) break;
         }
         if (st == ST_TRACE) {
+#ifdef RT_TRAV_SPEC
+          // speculative while-while: a lane that already holds leaves walks on (its second leaf set) for as long as
+          // some lane of the warp still searches its first leaf — it would sit idle in those steps otherwise
+          TravLeaves lv{0, 0, 0, 0}, lw{0, 0, 0, 0};
+#pragma unroll 1
+          for (int steps = 0; steps < R.trav_burst; ++steps) {
+            if (!__any_sync(tt, tv.cur >= 0 && lv.a == 0)) break;
+            if (tv.cur >= 0 && (lv.a == 0 || lw.a == 0)) {
+              TravLeaves nw{0, 0, 0, 0};
+              trav_inner(S, bp, tv, stack, nw);
+              if (lv.a == 0) lv = nw; else lw = nw;
+            }
+          }
+          if (lv.a != 0) trav_leaves2(S, ps.ray, bp, tv, lv, lw);
+#else
           int steps = 0;
           TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1 // unrolled copies of the node visit cost more instruction cache than they save
           while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
           if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
+#endif
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
@@ -1019,8 +1082,9 @@ __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int bl
 
 template <int KIND>
 __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevScene S, const RenderParams R) {
-  __shared__ ListSmem sm;
-  const SmemList L = stage_list<KIND>(S, sm);
+  __shared__ ListSmemData sm_data;
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
@@ -1265,8 +1329,9 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
 template <int KIND>
 __global__ void __launch_bounds__(256) k_trace_primary(const DevScene S, const RenderParams R, int* obj_id, float* t_out,
                                                        float* normal, uint8_t* front) {
-  __shared__ ListSmem sm;
-  const SmemList L = stage_list<KIND>(S, sm);
+  __shared__ ListSmemData sm_data;
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   const int tx = (R.x0 / kTile) + blockIdx.x, ty = (R.y0 / kTile) + blockIdx.y;
   int lx, ly;
   tile_pixel(threadIdx.x, lx, ly);
@@ -1341,7 +1406,7 @@ static cudaError_t launch_persistent(K kernel, const DevScene& S, const RenderPa
 template <int KIND, int NS, int BLOCKS>
 static cudaError_t launch_wq(const DevScene& S, const RenderParams& R, long long ctas_of_work, int sms, cudaStream_t st) {
   auto kernel = k_render_wq<KIND, NS, BLOCKS>;
-  const int smem = (int)((KIND == BVH_LIST ? sizeof(ListSmem) : 0) + 8 * sizeof(WqWarp<NS>));
+  const int smem = (int)((KIND == BVH_LIST ? sizeof(ListSmemData) : 0) + 8 * sizeof(WqWarp<NS>));
   static cudaError_t attr = [&]() {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;

@@ -740,10 +740,6 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
       if (P[i].type == OBJ_SPHERE) {
         for (int a = 0; a < 3; ++a) S.sph_cmax = std::max(S.sph_cmax, std::fabs(P[i].q[a]));
         S.sph_r2max = std::max(S.sph_r2max, (float)(P[i].r * P[i].r));
-      } else if (P[i].aa) { // ... and of the axis-aligned quad loops' hoisted error bound
-        int K;
-        std::memcpy(&K, &P[i].aa2.y, sizeof(int));
-        S.aa_cmax[K] = std::max(S.aa_cmax[K], std::fabs(P[i].aa1.x));
       }
   } else if (kind == BVH_REFERENCE) {
     // node 0 = super-root: the reference tests the root's own box first (bvh.ts:130)

@@ -19,7 +19,6 @@ struct HostScene {
   int planar_any = 0;
   int list_n[6] = {0, 0, 0, 0, 0, 0}; // LIST: slots per kind (spheres, aa-quads x/y/z, quads, planes)
   float sph_cmax = 0, sph_r2max = 0;  // LIST: max |centre component| and max r^2 over the spheres
-  float aa_cmax[3] = {0, 0, 0};       // LIST: max |plane coordinate| of the axis-aligned quads per normal axis
   int max_depth = 0; // deepest leaf below node 0
   std::vector<Node> nodes;
   std::vector<F4> p0, p1, p2, p3;

@@ -110,7 +110,6 @@ struct DevScene {
   int planar_any; // scene has planes/quads
   int list_n[6];  // LIST: slots per kind, in slot order: spheres, axis-aligned quads x/y/z, general quads, planes
   float sph_cmax, sph_r2max; // LIST: max |centre component| and max r^2 over the spheres
-  float aa_cmax[3];          // LIST: max |plane coordinate| of the axis-aligned quads with normal along x / y / z
   uint32_t seed_lo, seed_hi;
 };
 

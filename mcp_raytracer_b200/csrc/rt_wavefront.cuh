@@ -164,8 +164,9 @@ RT_DEV void wf_bin(const DevScene& S, const WfBuffers& W, bool done, int id, flo
 template <int KIND>
 __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const RenderParams R, const WfBuffers W, int n_rays,
                                                       const int* q_in) {
-  __shared__ ListSmem sm;
-  const SmemList L = stage_list<KIND>(S, sm);
+  __shared__ ListSmemData sm_data;
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
   unsigned st_rays = 0;
   if (KIND != BVH_SAH) {
     // brute-force list / reference tree: one whole query per ray, grid-stride
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(256, 2) k_wf_extend(const DevScene S, const Re
 // -------------------------------------------------------------------------------------------------
 template <int KIND, int TAG>
 __global__ void __launch_bounds__(256) k_wf_shade(const DevScene S, const RenderParams R, const WfBuffers W, int n, const int* q_in) {
-  __shared__ ListSmem sm;
-  stage_list<KIND>(S, sm);
+  __shared__ ListSmemData sm_data;
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   unsigned st_paths = 0, st_bounces = 0;

@@ -40,12 +40,30 @@ def divideIntoRegions(imageWidth: int, imageHeight: int, count: int) -> List[Dic
     return regions
 
 
+def applySceneCameraOptions(sceneData: Dict[str, Any], camera: Optional[Dict[str, Any]]) -> Dict[str, Any]:
+    """`scene.camera` of the MCP `raytrace` tool (cameraOptionsSchema, src/mcp.ts:132-142) is accepted by the reference and then
+    dropped: generateScene reads only scene.type / options / render (src/scenes/scenes.ts:52-55).  This maps it onto the fields
+    the renderer does read, so the tool's documented camera options take effect (TypeScript twin: ts/nativeCamera.ts)."""
+    if not camera:
+        return sceneData
+    cam = dict(sceneData.get("camera") or {})
+    render = dict(sceneData.get("render") or {})
+    for src, dst in (("vfov", "vfov"), ("lookFrom", "from"), ("lookAt", "at"), ("vUp", "up")):
+        if camera.get(src) is not None:
+            cam[dst] = camera[src]
+    for src, dst in (("imageWidth", "width"), ("aspectRatio", "aspect"), ("samples", "samples"), ("adaptiveTolerance", "aTolerance"),
+                     ("adaptiveBatchSize", "aBatch")):
+        if camera.get(src) is not None:
+            render[dst] = camera[src]
+    return {**sceneData, "camera": cam, "render": render}
+
+
 def renderScene(sceneConfig: Dict[str, Any], options: Optional[Dict[str, Any]] = None):
     """Everything `generateImageBuffer` does before PNG encoding: returns (rgb8[H,W,3], RenderStats)."""
     options = options or {}
     parallel = options.get("parallel", False)
     verbose = options.get("verbose", False)
-    sceneData = generateSceneData(sceneConfig)
+    sceneData = applySceneCameraOptions(generateSceneData(sceneConfig), sceneConfig.get("camera"))
     render = sceneConfig.get("render")
     ndev = _native.lib().rt_device_count()
     threads = options.get("threads") or ndev  # "threads" = number of GPUs here

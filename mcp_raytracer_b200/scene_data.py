@@ -166,11 +166,115 @@ def render_opts_struct(o: Dict[str, Any]) -> rt_render_opts:
         device=int(o["device"]), part_index=int(o["partIndex"]), part_count=int(o["partCount"]),
     )
 
+_OBJ_NAMES = {v: k for k, v in _OBJ_TYPES.items()}
+
+
+class SoAMaterials:
+    """`SceneData.materials` held as arrays (the material node table of rt_scene_desc) that still READS like the
+    reference's list of `{id, material}` records (src/scenes/sceneData.ts:76-110): len(), iteration and indexing build
+    the dicts on demand.  Large procedural scenes (100 000 rain drops = 100 001 materials) are generated straight into
+    this form, so handing them to the C ABI costs no per-object Python work; arbitrary SceneData keeps the dict walk.
+
+    type/color/param/child: node table (children precede parents); `roots` = node index of each named material;
+    `ids(k)` = its id string."""
+
+    def __init__(self, type_, color, param, child, roots, ids):
+        self.type = np.ascontiguousarray(type_, np.uint8)
+        self.color = np.ascontiguousarray(color, np.float64).reshape(-1, 3)
+        self.param = np.ascontiguousarray(param, np.float64)
+        self.child = np.ascontiguousarray(child, np.int32).reshape(-1, 2)
+        self.roots = np.ascontiguousarray(roots, np.int32)
+        self._ids = ids  # callable k -> str
+
+    def __len__(self) -> int:
+        return int(self.roots.shape[0])
+
+    def node_dict(self, i: int) -> Dict[str, Any]:
+        t = int(self.type[i])
+        c = [float(x) for x in self.color[i]]
+        if t == RT_MAT_LAMBERT:
+            return {"type": "lambert", "color": c}
+        if t == RT_MAT_METAL:
+            return {"type": "metal", "color": c, "fuzz": float(self.param[i])}
+        if t == RT_MAT_GLASS:
+            return {"type": "glass", "ior": float(self.param[i])}
+        if t == RT_MAT_LIGHT:
+            return {"type": "light", "emit": c}
+        if t == RT_MAT_MIXED:
+            return {"type": "mixed", "diff": self.node_dict(int(self.child[i, 0])), "spec": self.node_dict(int(self.child[i, 1])), "weight": float(self.param[i])}
+        return {"type": "layered", "inner": self.node_dict(int(self.child[i, 0])), "outer": self.node_dict(int(self.child[i, 1]))}
+
+    def id_of(self, k: int) -> str:
+        return self._ids(k)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        return {"id": self._ids(k), "material": self.node_dict(int(self.roots[k]))}
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+    def tolist(self) -> List[Dict[str, Any]]:
+        return list(self)
+
+
+class SoAObjects:
+    """`SceneData.objects` as arrays; reads like the reference's list of SceneObject records
+    (src/scenes/sceneData.ts:40-70).  material[k] = index into `materials` (a SoAMaterials)."""
+
+    def __init__(self, type_, pos, u, v, r, material, light, materials: SoAMaterials):
+        n = len(type_)
+        self.type = np.ascontiguousarray(type_, np.uint8)
+        self.pos = np.ascontiguousarray(pos, np.float64).reshape(n, 3)
+        self.u = np.ascontiguousarray(u, np.float64).reshape(n, 3)
+        self.v = np.ascontiguousarray(v, np.float64).reshape(n, 3)
+        self.r = np.ascontiguousarray(r, np.float64).reshape(n)
+        self.material = np.ascontiguousarray(material, np.int32).reshape(n)
+        self.light = np.ascontiguousarray(light, np.uint8).reshape(n)
+        self.materials = materials
+
+    def __len__(self) -> int:
+        return int(self.type.shape[0])
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        if k < 0:
+            k += len(self)
+        if not 0 <= k < len(self):
+            raise IndexError(k)
+        t = int(self.type[k])
+        ob: Dict[str, Any] = {"type": _OBJ_NAMES[t], "pos": [float(x) for x in self.pos[k]]}
+        if t == RT_OBJ_SPHERE:
+            ob["r"] = float(self.r[k])
+        else:
+            ob["u"] = [float(x) for x in self.u[k]]
+            ob["v"] = [float(x) for x in self.v[k]]
+        ob["material"] = self.materials.id_of(int(self.material[k]))
+        if self.light[k]:
+            ob["light"] = True
+        return ob
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+    def tolist(self) -> List[Dict[str, Any]]:
+        return list(self)
+
 
 class FlatScene:
     """Owns the numpy arrays behind an `rt_scene_desc` (keeps them alive)."""
 
     def __init__(self, sceneData: Dict[str, Any]):
+        objs0 = sceneData["objects"]
+        if isinstance(objs0, SoAObjects) and sceneData.get("materials") is objs0.materials:
+            self._from_arrays(objs0, sceneData)  # array-backed scene from a generator: nothing to walk
+            return
         materials: Dict[str, Any] = {}
         for m in sceneData.get("materials") or []:  # scenes.ts:62-65
             materials[m["id"]] = m["material"]
@@ -225,6 +329,25 @@ class FlatScene:
         self.mat_param_a = np.asarray(self.mat_param, np.float64)
         self.mat_child_a = np.asarray(self.mat_child, np.int32).reshape(-1, 2)
 
+        self._finish(sceneData, n)
+
+    def _from_arrays(self, objs: "SoAObjects", sceneData: Dict[str, Any]) -> None:
+        """Array-backed SceneData: no per-object Python work.  The checks the dict walk makes per record
+        (scenes.ts:137, :154, :178) run vectorised; the C side validates the node table again."""
+        m = objs.materials
+        n = len(objs)
+        if n and int(objs.type.max()) > RT_OBJ_QUAD:
+            raise RaytracerError(f"Unknown object type: {int(objs.type.max())}")
+        if len(m.type) and int(m.type.max()) > RT_MAT_LAYERED:
+            raise RaytracerError(f"Unknown material type: {int(m.type.max())}")
+        if n and (int(objs.material.min()) < 0 or int(objs.material.max()) >= len(m)):
+            raise RaytracerError(f"Material not found: {int(objs.material.max())}")
+        self.obj_type, self.obj_pos, self.obj_u, self.obj_v, self.obj_r, self.obj_light = objs.type, objs.pos, objs.u, objs.v, objs.r, objs.light
+        self.obj_material = np.ascontiguousarray(m.roots[objs.material], np.int32)  # object -> root node of its material
+        self.mat_type_a, self.mat_color_a, self.mat_param_a, self.mat_child_a = m.type, m.color, m.param, m.child
+        self._finish(sceneData, n)
+
+    def _finish(self, sceneData: Dict[str, Any], n: int) -> None:
         cam = dict(DEFAULT_CAMERA_OPTIONS)
         cam.update({k: v for k, v in (sceneData.get("camera") or {}).items() if v is not None})
         bg = cam["background"]

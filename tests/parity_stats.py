@@ -83,7 +83,7 @@ def compare_converged(g_mean: np.ndarray, g_var: np.ndarray, n_g: int, o_mean: n
     return out
 
 
-def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002) -> None:
+def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002, one_percent_bar: bool = True) -> None:
     """The asserted bars (every number RAW, nothing subtracted):
     * per pixel |gpu - oracle| <= 3 sigma for >= 99.73 % - `firefly_allowance` of the channels (a Gaussian leaves
       0.27 % outside; heavy-tailed radiance makes the sample variance an underestimate on a few pixels), and
@@ -92,7 +92,8 @@ def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002) -> None
       z-score lies in [0.85, 1.15] (a bias of 0.4 sigma anywhere near the image's energy would break it);
     * the 1 % bar: raw relative RMSE <= 1 % on the 8x8 and 16x16 box-filtered images (per-pixel noise at
       ~1000 spp is 1-4 % in EITHER implementation, so a per-pixel 1 % is not a statement about parity; averaging
-      64 pixels divides noise by 8 and leaves any bias in place);
+      64 pixels divides noise by 8 and leaves any bias in place); `one_percent_bar=False` (renders of ~100 spp, where
+      even the filtered noise is above 1 %) asserts instead that the filtered RMSE is explained by noise;
     * whole-image mean radiance within 0.5 % per channel;
     * channels without Monte-Carlo variance (flat background, unlit pixels) agree to FP32 rounding."""
     assert r["frac_within_3sigma"] >= 0.9973 - firefly_allowance, r
@@ -101,7 +102,10 @@ def check_converged(r: Dict[str, Any], firefly_allowance: float = 0.002) -> None
     assert 0.85 <= r["z2_mean"] <= 1.15, r
     for b in ("8", "16"):
         if b in r["rel_rmse_block"]:
-            assert r["rel_rmse_block"][b] <= 0.01, r
+            if one_percent_bar:
+                assert r["rel_rmse_block"][b] <= 0.01, r
+            else:  # too few samples for noise to drop under 1 % even after filtering: the filtered RMSE is still all noise
+                assert r["rel_rmse_block"][b] <= 1.15 * r["rel_rmse_block_noise_floor"][b] + 1e-6, r
     for a, b in zip(r["mean_gpu"], r["mean_oracle"]):
         assert abs(a - b) <= 0.005 * abs(b) + 1e-6, r
     assert r["quiet_max_excess"] <= 0.0, r                                # flat-colour channels agree to FP32 rounding

@@ -65,9 +65,10 @@ def run_converged_case(name, threads=THREADS):
               "gpu_paths": st.samples["total"], "oracle_paths": int(o["stats"].samples_total), "oracle_threads": threads,
               "bounces_avg_gpu": st.bounces["avg"], "bounces_avg_oracle": o["stats"].bounces_total / max(1, o["stats"].samples_total)})
     # RGB8 after gamma: the two images differ by Monte-Carlo noise only.  d(255.999 sqrt(c)) = 128 dc / sqrt(c).
-    sigma = np.sqrt(g_var / n_g + o_var / n_o)
-    expected = 128.0 * np.sqrt(2 / np.pi) * sigma / np.sqrt(np.maximum(o_mean, 1e-3))
-    r["rgb8_mean_abs_diff"] = float(np.mean(np.abs(rgb.astype(int) - o["rgb8"].astype(int))))
+    fin = np.isfinite(o_mean).all(axis=-1) & np.isfinite(o_var).all(axis=-1)  # pixels the reference poisons with a NaN sample are black there
+    sigma = np.sqrt(g_var[fin] / n_g + o_var[fin] / n_o)
+    expected = 128.0 * np.sqrt(2 / np.pi) * sigma / np.sqrt(np.maximum(o_mean[fin], 1e-3))
+    r["rgb8_mean_abs_diff"] = float(np.mean(np.abs(rgb[fin].astype(int) - o["rgb8"][fin].astype(int))))
     r["rgb8_mean_abs_diff_predicted"] = float(np.mean(expected))
     return r
 
@@ -178,5 +179,5 @@ def run_c4_converged(width=80, n_g=128, n_o=256, threads=THREADS):
 def test_c4_full_depth_statistics_through_the_deep_tree_kernels(gpu):
     r = run_c4_converged()
     print(json.dumps(r))
-    ps.check_converged(r)
+    ps.check_converged(r, one_percent_bar=False)  # 128 / 256 spp: the 3-sigma, z-score and noise-floor bars carry the statement
     assert abs(r["bounces_avg_gpu"] - r["bounces_avg_oracle"]) <= 0.01 * r["bounces_avg_oracle"]

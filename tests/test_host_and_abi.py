@@ -300,3 +300,32 @@ def test_gloo_world_size_2_gather_and_stats(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert "GATHER_OK" in outs[0]
+
+
+def test_napi_shim_compiles_against_the_stub_header():
+    """ts/addon/rt_napi.c cannot be built here (no node, no node_api.h); it is type-checked against a stub of the Node-API
+    prototypes it uses, and against the real include/rt_b200.h: argument counts and types of every rt_* call are verified."""
+    cmd = ["gcc", "-fsyntax-only", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "ts", "addon", "stub"),
+           "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "ts", "addon", "rt_napi.c")]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode == 0, r.stdout.decode()
+    src = open(os.path.join(ROOT, "ts", "addon", "rt_napi.c")).read()
+    for fn in ("rt_camera_create", "rt_multi_create", "rt_camera_render_region", "rt_multi_render_region", "rt_camera_destroy", "rt_multi_destroy",
+               "napi_async_work", "napi_adjust_external_memory"):
+        assert fn in src, fn
+
+
+def test_scene_camera_options_of_the_mcp_tool_take_effect():
+    """src/mcp.ts:132-142 accepts scene.camera and the reference drops it; the native dispatch applies it."""
+    from mcp_raytracer_b200 import generateSceneData, validateScene
+    from mcp_raytracer_b200.raytracer import applySceneCameraOptions
+
+    sd = generateSceneData({"type": "cornell"})
+    out = applySceneCameraOptions(sd, {"imageWidth": 320, "aspectRatio": 2.0, "vfov": 55, "lookFrom": [1, 2, 3], "lookAt": [0, 0, 1], "vUp": [0, 0, 1],
+                                       "samples": 7, "adaptiveTolerance": 0.2, "adaptiveBatchSize": 4})
+    assert out["camera"]["vfov"] == 55 and out["camera"]["from"] == [1, 2, 3] and out["camera"]["at"] == [0, 0, 1] and out["camera"]["up"] == [0, 0, 1]
+    assert out["render"]["width"] == 320 and out["render"]["aspect"] == 2.0 and out["render"]["samples"] == 7
+    assert out["render"]["aTolerance"] == 0.2 and out["render"]["aBatch"] == 4
+    assert sd["camera"]["vfov"] != 55 and applySceneCameraOptions(sd, None) is sd   # the input is not modified
+    rep = validateScene(out, None)
+    assert rep["errors"] == 0

@@ -4,6 +4,8 @@
  * that IS exercised by the test-suite: mcp_raytracer_b200/scene_data.py (flattening) and
  * mcp_raytracer_b200/camera.py (Camera over the C ABI).
  *
+ * NOT COMPILED HERE (no tsc); the N-API shim it loads is syntax-checked against a stub header (ts/addon/rt_napi.c).
+ *
  * Usage inside the reference: in src/scenes/scenes.ts `createCameraFromSceneData` return
  * `new NativeCamera(sceneData, renderOptions)` instead of building Hittables + BVHNode + Camera;
  * `camera.render(pixelData)` / `camera.renderRegion(pixelData, region)` keep their signatures
@@ -71,27 +73,59 @@ export function flattenScene(sceneData: SceneData) {
   };
 }
 
+/** `scene.camera` of the MCP `raytrace` tool (cameraOptionsSchema, src/mcp.ts:132-142) is accepted by the reference and then
+ *  DROPPED: generateScene only reads scene.type / options / render (src/scenes/scenes.ts:52-55).  This maps it onto the fields
+ *  the renderer does read, so the tool's documented camera options take effect (SURVEY.md §8f row 4).  Python mirror:
+ *  mcp_raytracer_b200/raytracer.py applySceneCameraOptions. */
+export function applySceneCameraOptions(sceneData: SceneData, cam?: Record<string, any>): SceneData {
+  if (!cam) return sceneData;
+  const camera = { ...sceneData.camera }, render: Record<string, any> = { ...(sceneData.render ?? {}) };
+  if (cam.vfov !== undefined) camera.vfov = cam.vfov;
+  if (cam.lookFrom !== undefined) camera.from = cam.lookFrom;
+  if (cam.lookAt !== undefined) camera.at = cam.lookAt;
+  if (cam.vUp !== undefined) camera.up = cam.vUp;
+  if (cam.imageWidth !== undefined) render.width = cam.imageWidth;
+  if (cam.aspectRatio !== undefined) render.aspect = cam.aspectRatio;
+  if (cam.samples !== undefined) render.samples = cam.samples;
+  if (cam.adaptiveTolerance !== undefined) render.aTolerance = cam.adaptiveTolerance;
+  if (cam.adaptiveBatchSize !== undefined) render.aBatch = cam.adaptiveBatchSize;
+  return { ...sceneData, camera, render };
+}
+
+type NativeOpts = { seed?: number, device?: number, partIndex?: number, partCount?: number, nDevices?: number };
+
+/** One GPU (`multi` false) or every visible GPU inside one call (`multi` true: rt_multi_*, the native stand-in for the
+ *  worker pool of src/raytracer.ts:60-90).  Same `render` / `renderRegion` signatures as src/camera.ts:388,439. */
 export class NativeCamera {
   readonly imageWidth: number; readonly imageHeight: number; readonly channels = 3;
   private handle: unknown; private flat: ReturnType<typeof flattenScene>;
-  constructor(sceneData: SceneData, renderOptions: RenderOptions = {}, native: { seed?: number, device?: number, partIndex?: number, partCount?: number } = {}) {
+  constructor(sceneData: SceneData, renderOptions: RenderOptions = {}, native: NativeOpts = {}, multi = false) {
     const o = { width: 400, aspect: 16 / 9, samples: 100, aTolerance: 0.05, aBatch: 10, mode: 'default', depth: 100, roulette: true, rouletteDepth: 3,
                 ...sceneData.render, ...renderOptions };   // src/camera.ts:73-83,116 ; src/scenes/scenes.ts:97-100
     this.flat = flattenScene(sceneData);
-    this.handle = addon.createCamera(this.flat, { ...o, roulette: o.roulette ? 1 : 0, mode: MODE[o.mode as keyof typeof MODE],
-      seed: native.seed ?? 0, device: native.device ?? -1, partIndex: native.partIndex ?? 0, partCount: native.partCount ?? 1 });
+    const opts = { ...o, roulette: o.roulette ? 1 : 0, mode: MODE[o.mode as keyof typeof MODE],
+      seed: native.seed ?? 0, device: native.device ?? -1, partIndex: native.partIndex ?? 0, partCount: native.partCount ?? 1 };
+    this.handle = multi ? addon.createMulti(this.flat, opts, native.nDevices ?? 0) : addon.createCamera(this.flat, opts);
     const info = addon.cameraInfo(this.handle);
     this.imageWidth = info.imageWidth; this.imageHeight = info.imageHeight;
   }
-  renderRegion(buffer: Uint8ClampedArray, region: RenderRegion): RenderStats {
-    const s = addon.renderRegion(this.handle, region, buffer);
+  private static stats(s: any): RenderStats {
     const r = new RenderStats();
     r.pixels = s.pixels; r.samples.total = s.samplesTotal; r.bounces.total = s.bouncesTotal;
     if (s.pixels > 0) { r.samples.min = s.samplesMin; r.samples.max = s.samplesMax; r.bounces.min = s.bouncesMin; r.bounces.max = s.bouncesMax; r.samples.avg = s.samplesTotal / s.pixels; }
     if (s.samplesTotal > 0) r.bounces.avg = s.bouncesTotal / s.samplesTotal;
     return r;
   }
+  renderRegion(buffer: Uint8ClampedArray, region: RenderRegion): RenderStats {
+    return NativeCamera.stats(addon.renderRegion(this.handle, region, buffer));
+  }
   render(pixelData: Uint8ClampedArray): RenderStats {
     return this.renderRegion(pixelData, { x: 0, y: 0, width: this.imageWidth, height: this.imageHeight });
   }
+  /** The render on a libuv worker (napi_async_work): generateImageBuffer stays `async` without blocking the event loop. */
+  async renderAsync(pixelData: Uint8ClampedArray): Promise<RenderStats> {
+    return NativeCamera.stats(await addon.renderRegionAsync(this.handle, { x: 0, y: 0, width: this.imageWidth, height: this.imageHeight }, pixelData));
+  }
+  /** Release the GPU memory now (the reference builds a camera per request: do not wait for the GC). */
+  destroy(): void { addon.destroyCamera(this.handle); }
 }
