@@ -67,13 +67,44 @@ def make_scene(kind, options):
 # algorithmic work model — SURVEY.md §8(d): flops the REFERENCE algorithm spends, with event
 # counts taken from the oracle walking the reference's own BVH topology.
 # ------------------------------------------------------------------------------------------
+def shading_flops(cnt, n_lights, aperture):
+    """The per-path part of the model: everything except the closest-hit queries."""
+    lambert = 110 if n_lights == 0 else 200 + 90 * (n_lights - 1)
+    return ((31 + (25 if aperture > 0 else 0)) * cnt["paths"] + 8 * cnt["rr"] + 24 * cnt["background"] + lambert * cnt["lambert"]
+            + 62 * cnt["metal"] + 35 * cnt["metal_fuzz0"] + 60 * cnt["dielectric"] + 6 * cnt["hits"])
+
+
 def algorithmic_flops(cnt, n_lights, aperture):
     ray = (21 * cnt["box_tests"] + 23 * cnt["sphere_miss"] + 52 * cnt["sphere_hit"] + 16 * cnt["planar_treject"]
            + 57 * cnt["quad_outside"] + 72 * cnt["quad_hit"] + 28 * cnt["plane_hit"])
-    lambert = 110 if n_lights == 0 else 200 + 90 * (n_lights - 1)
-    path = ((31 + (25 if aperture > 0 else 0)) * cnt["paths"] + 8 * cnt["rr"] + 24 * cnt["background"] + lambert * cnt["lambert"]
-            + 62 * cnt["metal"] + 35 * cnt["metal_fuzz0"] + 60 * cnt["dielectric"] + 6 * cnt["hits"])
-    return ray + path
+    return ray + shading_flops(cnt, n_lights, aperture)
+
+
+def executed_events(workload, ropts, spp):
+    """Node visits and primitive tests the DEVICE executes on its own tree, counted by the instrumented build of the library
+    (csrc/libmcprt_b200_count.so, -DRT_COUNT_EVENTS) in a process of its own: one render at `spp` samples, never timed.
+    None when that build is absent."""
+    lib = os.path.join(ROOT, "mcp_raytracer_b200", "csrc", "libmcprt_b200_count.so")
+    if not os.path.exists(lib):
+        return None
+    code = (
+        "import json, sys, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "import bench\n"
+        "from mcp_raytracer_b200 import createCameraFromSceneData, _native\n"
+        f"label, kind, sopts, ro = bench.WORKLOADS[{workload!r}]\n"
+        f"ro = dict(ro, **{json.dumps({k: v for k, v in ropts.items()})}, samples={int(spp)}, integrator='megakernel')\n"
+        "assert _native.lib().rt_counts_events() == 1\n"
+        "sd = bench.make_scene(kind, sopts)\n"
+        "with createCameraFromSceneData(sd, ro) as cam:\n"
+        "    st = cam.render(np.zeros(cam.imageWidth * cam.imageHeight * 3, np.uint8))\n"
+        "print(json.dumps({'paths': st.samples['total'], 'rays': st.rays, 'node_visits': st.nodeVisits, 'prim_tests': st.primTests}))\n"
+    )
+    try:
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, RT_B200_LIB=lib), capture_output=True, text=True, timeout=600)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
 
 
 def cpu_reference_run(sd, opts, target_seconds, threads):
@@ -189,7 +220,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="C2", help="one of %s, or a comma-separated list (one JSON line each)" % ", ".join(WORKLOADS))
     ap.add_argument("--samples", type=int, default=None, help="override spp (development only; the default is the BASELINE config)")
     ap.add_argument("--width", type=int, default=None, help="override width (development only)")
     ap.add_argument("--bvh", default="auto")
@@ -215,7 +246,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    label, kind, scene_opts, ropts = WORKLOADS[args.workload]
+    env = {"group": False}
+    rc = 0
+    for wl in args.workload.split(","):  # one JSON line per workload (the default, C2, prints exactly one)
+        rc |= bench_workload(args, wl, rank, world, local_rank, emit, env)
+    if env["group"]:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return rc
+
+
+def bench_workload(args, workload, rank, world, local_rank, emit, env):
+    label, kind, scene_opts, ropts = WORKLOADS[workload]
     ropts = dict(ropts)
     overridden = False
     if args.samples:
@@ -266,8 +309,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    if world > 1 and not env["group"]:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        env["group"] = True
 
     def barrier():
         if world > 1:
@@ -291,7 +335,7 @@ def main():
     else:
         fb = torch.zeros((H, W, 3), dtype=torch.uint8, device=dev)
         fb_ptr = fb.data_ptr()
-    stats_dev = torch.zeros(64, dtype=torch.uint8, device=dev)
+    stats_dev = torch.zeros(80, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     host_fb = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
 
@@ -299,7 +343,7 @@ def main():
         import ctypes
 
         raw = bytes(stats_dev.cpu().numpy())
-        assert ctypes.sizeof(rt_stats) == 64 == len(raw)
+        assert ctypes.sizeof(rt_stats) == 80 == len(raw)
         return rt_stats.from_buffer_copy(raw)
 
     def step_device():
@@ -401,15 +445,13 @@ def main():
     fs = FlatScene(sd)
     h2d = int(sum(a.nbytes for a in (fs.obj_type, fs.obj_pos, fs.obj_u, fs.obj_v, fs.obj_r, fs.obj_material, fs.obj_light,
                                      fs.mat_type_a, fs.mat_color_a, fs.mat_param_a, fs.mat_child_a)))
-    d2h = W * H * 3 + 64
+    d2h = W * H * 3 + 80
 
     if rank != 0:
         cam.close()
         if shared:
             dist.barrier()
             shared.close()
-        if world > 1:
-            dist.destroy_process_group()
         return 0
 
     value = paths_per_step * args.steps / (total_ms * 1e-3) / 1e6
@@ -438,13 +480,34 @@ def main():
         hbm_bytes = W * H * 3 + h2d  # compulsory traffic: scene once + RGB8 out
         roof = {
             "bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": measured_traffic(args.workload, world, overridden),
+            "traffic": measured_traffic(workload, world, overridden),
             "peak_source": f"FP32 FFMA microbenchmark in this run (rt_measure_fp32_peak): {fp32_peak:.1f} TFLOP/s per GPU at <= {sm_attr_mhz:.0f} MHz; "
                            "MEASURED_PEAKS.json holds HBM/bf16 peaks only",
             "flops_per_path": flops_per_path, "flops_model": "SURVEY.md §8d, event counts from the oracle walking the reference BVH",
             "hbm": {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / kernel_s / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "note": "scene is register/L1-resident; HBM is not the bound"},
         }
+        roof["algorithmic_frac"] = roof["frac"]
+        # What the device EXECUTES on its own structure (instrumented build, separate process, reduced spp): wide-node visits
+        # (4 child boxes, 21 flop each) and primitive tests (23 flop, +29 for the one that hits), plus the model's per-path
+        # shading part.  On tree scenes the reference's median-split tree and per-axis box rule make the algorithmic figure
+        # count boxes no sensible tree visits (rain 100k: ~6000 per ray), so there `frac` is the executed figure and the
+        # reference-tree one stays beside it.
+        ev = executed_events(workload, {k: v for k, v in ropts.items() if k in ("width", "depth", "bvh")}, max(1, min(int(ropts["samples"]), 8)))
+        if ev and ev["paths"]:
+            cnt = c["counters"]
+            shade = shading_flops(cnt, c["n_lights"], float(sd["camera"].get("aperture", 0))) / max(1, cnt["paths"])
+            hit_frac = cnt["hits"] / max(1, cnt["rays"])
+            ray_flops = (84.0 * ev["node_visits"] + 23.0 * ev["prim_tests"] + 29.0 * hit_frac * ev["rays"]) / ev["paths"]
+            ex = (ray_flops + shade) * paths_per_step / kernel_s / 1e12
+            roof["executed"] = {"achieved": ex, "frac": ex / peak, "flops_per_path": ray_flops + shade,
+                                "node_visits_per_ray": ev["node_visits"] / max(1, ev["rays"]), "prim_tests_per_ray": ev["prim_tests"] / max(1, ev["rays"]),
+                                "counted_at_spp": max(1, min(int(ropts["samples"]), 8)),
+                                "source": "libmcprt_b200_count.so (same kernels with counters), one untimed render in its own process"}
+            if cam.info.bvh_kind != 3:
+                roof["reference_tree"] = {"achieved": roof["achieved"], "frac": roof["frac"], "flops_per_path": flops_per_path}
+                roof["achieved"], roof["frac"], roof["flops_per_path"] = ex, ex / peak, ray_flops + shade
+                roof["flops_model"] = "SURVEY.md §8d constants on the events the device executes on its own 4-wide SAH tree; reference-tree figure under reference_tree"
 
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -472,8 +535,6 @@ def main():
     if shared:
         dist.barrier()
         shared.close()
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 

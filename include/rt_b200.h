@@ -160,6 +160,10 @@ typedef struct rt_stats {
   double device_ms;     /* CUDA-event time of the render kernels on the camera's stream */
   int32_t kernel_launches; /* kernels of this library launched by the call */
   int32_t reserved;
+  /* executed traversal work, filled ONLY by the instrumented build of the library (libmcprt_b200_count.so,
+   * -DRT_COUNT_EVENTS; rt_counts_events() == 1), 0 otherwise: the roofline's "executed" figure for tree scenes */
+  uint64_t node_visits;  /* wide-node visits (four child-box tests each) */
+  uint64_t prim_tests;   /* primitive tests (always-tested prefix + leaves; LIST: every slot for every ray) */
 } rt_stats;
 
 /* Derived camera state, for host-side mirrors of the reference's public Camera fields
@@ -214,6 +218,19 @@ rt_status rt_camera_render_region_device(rt_camera* cam, const rt_region* region
 rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint8_t* rgb8,
                                    size_t rgb8_len, float* linear_rgb, float* moments,
                                    rt_stats* stats);
+
+/* ---- progressive output ----
+ * The reference renders every pixel to completion before anything is visible (src/camera.ts:400-423) and has no preview
+ * surface.  This call delivers the SAME image as rt_camera_render_region in n_passes steps: after pass k every pixel holds
+ * its first ceil(samples * k / n_passes) samples (adaptive sampling: rounded up to a multiple of aBatch, pixels that have
+ * converged stop for good, exactly where the one-shot render stops them), the host buffers are refreshed, and `on_pass` is
+ * called with the statistics so far; a non-zero return ends the render early.  Fixed-spp passes add sample windows to the
+ * exact fixed-point sums, the pixel-stream kernels keep each pixel's PixelStats on the device between passes, and the
+ * random streams are keyed by (pixel, sample): the final image is bit-identical to the one-shot render.  Synchronous. */
+typedef int32_t (*rt_progress_fn)(void* user, int32_t pass, int32_t n_passes, int32_t samples_per_pixel_cap, const rt_stats* so_far);
+rt_status rt_camera_render_progressive(rt_camera* cam, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
+                                       float* linear_rgb, int32_t n_passes, rt_progress_fn on_pass, void* user,
+                                       rt_stats* stats);
 
 /* ---- parity hook: primary visibility through pixel centres (getRay with no jitter and
  * no defocus, src/camera.ts:176-196) + closest hit over (0.001, inf) (src/camera.ts:249).
@@ -295,6 +312,7 @@ rt_status rt_debug_diffuse_bounce(rt_camera* cam, int32_t n, const double* p, co
 const char* rt_last_error(void);
 int32_t rt_device_count(void);
 int32_t rt_abi_version(void);
+int32_t rt_counts_events(void); /* 1 = instrumented build: node visits / primitive tests are counted into the stats (slower) */
 /* which part (0 <= part < part_count) renders pixel (x, y) of an image `image_width` wide: the partition rule of
  * rt_render_opts.part_index / rt_multi_*, for host code that assembles or checks partitioned renders. */
 int32_t rt_block_owner(int32_t x, int32_t y, int32_t image_width, int32_t part_count);

@@ -20,8 +20,8 @@ LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(CSRC, "libmcprt_b200.so
 EXPORTS = [
     "rt_camera_create", "rt_camera_destroy", "rt_camera_get_info", "rt_camera_set_stream",
     "rt_camera_render_region", "rt_camera_render", "rt_camera_render_region_device",
-    "rt_camera_render_moments", "rt_camera_trace_primary", "rt_last_error", "rt_device_count",
-    "rt_abi_version", "rt_block_owner", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
+    "rt_camera_render_moments", "rt_camera_render_progressive", "rt_camera_trace_primary", "rt_last_error", "rt_device_count",
+    "rt_abi_version", "rt_counts_events", "rt_block_owner", "rt_measure_fp32_peak", "rt_trim_device_cache", "rt_scene_validate",
     "rt_multi_create", "rt_multi_destroy", "rt_multi_get_info", "rt_multi_render_region",
     "rt_shared_buffer_create", "rt_shared_buffer_open", "rt_shared_buffer_release",
     "rt_debug_scatter", "rt_debug_get_ray", "rt_debug_light_pdf", "rt_debug_light_random_vec", "rt_debug_diffuse_bounce",
@@ -61,6 +61,7 @@ def lib() -> C.CDLL:
     L.rt_last_error.restype = C.c_char_p
     L.rt_device_count.restype = C.c_int32
     L.rt_abi_version.restype = C.c_int32
+    L.rt_counts_events.restype = C.c_int32
     L.rt_block_owner.restype = C.c_int32
     L.rt_block_owner.argtypes = [C.c_int32] * 4
     L.rt_camera_create.argtypes = [C.POINTER(rt_scene_desc), C.POINTER(rt_render_opts), C.POINTER(vp)]
@@ -71,6 +72,7 @@ def lib() -> C.CDLL:
     L.rt_camera_render.argtypes = [vp, vp, C.c_size_t, vp, C.POINTER(rt_stats)]
     L.rt_camera_render_region_device.argtypes = [vp, C.POINTER(rt_region), vp, vp, vp, vp]
     L.rt_camera_render_moments.argtypes = [vp, C.POINTER(rt_region), vp, C.c_size_t, vp, vp, C.POINTER(rt_stats)]
+    L.rt_camera_render_progressive.argtypes = [vp, C.POINTER(rt_region), vp, C.c_size_t, vp, C.c_int32, vp, vp, C.POINTER(rt_stats)]
     L.rt_camera_trace_primary.argtypes = [vp, C.POINTER(rt_region), vp, vp, vp, vp]
     L.rt_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.rt_trim_device_cache.restype = C.c_uint64

@@ -45,6 +45,8 @@ class RenderStats:
         self.rays = 0
         self.deviceMs = 0.0
         self.kernelLaunches = 0
+        self.nodeVisits = 0
+        self.primTests = 0
 
     @staticmethod
     def from_struct(s: rt_stats) -> "RenderStats":
@@ -63,6 +65,8 @@ class RenderStats:
         r.rays = int(s.rays)
         r.deviceMs = float(s.device_ms)
         r.kernelLaunches = int(s.kernel_launches)
+        r.nodeVisits = int(s.node_visits)   # instrumented build only (rt_counts_events)
+        r.primTests = int(s.prim_tests)
         return r
 
     @staticmethod
@@ -79,6 +83,8 @@ class RenderStats:
             m.rays += s.rays
             m.deviceMs = max(m.deviceMs, s.deviceMs)
             m.kernelLaunches += s.kernelLaunches
+            m.nodeVisits += getattr(s, "nodeVisits", 0)
+            m.primTests += getattr(s, "primTests", 0)
         if m.pixels > 0:
             m.samples["avg"] = m.samples["total"] / m.pixels
         if m.samples["total"] > 0:
@@ -179,6 +185,37 @@ class Camera:
 
     def render(self, pixelData: np.ndarray, linear: Optional[np.ndarray] = None) -> RenderStats:
         return self.renderRegion(pixelData, None, linear)
+
+    def renderProgressive(self, pixelData: np.ndarray, passes: int, onPass=None, region: Optional[Dict[str, int]] = None,
+                          linear: Optional[np.ndarray] = None) -> RenderStats:
+        """The image of `render`, delivered in `passes` growing prefixes of the samples (rt_camera_render_progressive).
+        onPass(pass, passes, samplesCap, RenderStats) is called after each pass with `pixelData` refreshed; return True to
+        stop early.  The reference has no preview surface."""
+        W, H = self.imageWidth, self.imageHeight
+        if pixelData is not None and (pixelData.dtype != np.uint8 or not pixelData.flags["C_CONTIGUOUS"]):
+            raise RaytracerError("pixel buffer must be a C-contiguous uint8 array")
+        if linear is not None and (linear.dtype != np.float32 or linear.size < W * H * 3):
+            raise RaytracerError("linear buffer must be float32 [H][W][3]")
+        reg = _region_struct(region, W, H)
+        st = rt_stats()
+        errors: List[BaseException] = []
+
+        @C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(rt_stats))
+        def cb(_user, k, n, cap, so_far):
+            if onPass is None:
+                return 0
+            try:
+                return 1 if onPass(int(k), int(n), int(cap), RenderStats.from_struct(so_far.contents)) else 0
+            except BaseException as e:  # noqa: BLE001 — never unwind through the C frame
+                errors.append(e)
+                return 1
+
+        self._check(_native.lib().rt_camera_render_progressive(
+            self._h, C.byref(reg), pixelData.ctypes.data if pixelData is not None else None, pixelData.nbytes if pixelData is not None else 0,
+            linear.ctypes.data if linear is not None else None, int(passes), C.cast(cb, C.c_void_p), None, C.byref(st)))
+        if errors:
+            raise errors[0]
+        return RenderStats.from_struct(st)
 
     def renderRegionDevice(self, region, rgb8_ptr: int = 0, linear_ptr: int = 0, moments_ptr: int = 0, stats_ptr: int = 0) -> None:
         """Enqueue on the camera's stream; device pointers; no synchronisation."""

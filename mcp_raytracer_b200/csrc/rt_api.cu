@@ -176,6 +176,7 @@ struct rt_camera {
   int* d_queue = nullptr;
   size_t queue_ints = 0;
   unsigned long long* d_scratch = nullptr; // fixed-point radiance sums [H][W][4]
+  PixState* d_pixstate = nullptr;          // progressive renders of the pixel-stream kernels: PixelStats between passes
   size_t scratch_elems = 0;
   int sms = 0;
   int chunks = 1;
@@ -215,7 +216,7 @@ static void free_camera(rt_camera* c) {
   cudaStreamSynchronize(c->stream); // the blocks go back to the cache: nothing of this camera may still be in flight
   for (void* p : c->allocs) dev_free(p);
   dev_free(c->d_rgb8); dev_free(c->d_linear); dev_free(c->d_moments); dev_free(c->d_ids);
-  dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch);
+  dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch); dev_free(c->d_pixstate);
   wf_release(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -239,7 +240,7 @@ static rt_status clip_region(const rt_camera* c, const rt_region* r, RenderParam
   return RT_OK;
 }
 
-static const unsigned long long kStatsInit[kStatCount] = {0, 0, 0, 0, 0x7fffffffull, 0, 0x7fffffffull, 0};
+static const unsigned long long kStatsInit[kStatCount] = {0, 0, 0, 0, 0x7fffffffull, 0, 0x7fffffffull, 0, 0, 0};
 
 static void unpack_stats(const unsigned long long* raw, rt_stats* s) {
   s->pixels = raw[kStatPixels];
@@ -250,12 +251,21 @@ static void unpack_stats(const unsigned long long* raw, rt_stats* s) {
   s->samples_max = (int32_t)raw[kStatSamplesMax];
   s->bounces_min = (int32_t)raw[kStatBouncesMin];
   s->bounces_max = (int32_t)raw[kStatBouncesMax];
+  s->node_visits = raw[kStatNodeVisits];
+  s->prim_tests = raw[kStatPrimTests];
 }
 
 extern "C" {
 
 const char* rt_last_error(void) { return g_err.c_str(); }
 int32_t rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+int32_t rt_counts_events(void) {
+#ifdef RT_COUNT_EVENTS
+  return 1;
+#else
+  return 0;
+#endif
+}
 int32_t rt_block_owner(int32_t x, int32_t y, int32_t image_width, int32_t part_count) {
   if (part_count <= 1 || x < 0 || y < 0 || image_width <= 0) return 0;
   return block_owner(x / 8, y / 4, (image_width + 7) / 8, part_count);
@@ -581,8 +591,13 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
   return RT_OK;
 }
 
+// One pass of a progressive render (rt_camera_render_progressive); null = the whole render in one launch.
+struct ProgPass {
+  int s0, s1;   // fixed spp: samples [s0, s1) of every pixel; pixel stream: s0 = the previous cap, s1 = this pass's cap
+  bool first;   // first pass: the accumulators start from zero
+};
 // enqueue: stats init, render kernel, optional stats finalisation.  No synchronisation.
-static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_dev, int* launches) {
+static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_dev, int* launches, const ProgPass* pass = nullptr) {
   CU(cudaMemcpyAsync(c->d_stats, kStatsInit, sizeof(kStatsInit), cudaMemcpyHostToDevice, c->stream));
   P.stats = c->d_stats;
   *launches = 0;
@@ -602,6 +617,20 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       P.chunks = (int)std::min<long long>(std::max<long long>(k, 1), 64);
     }
     if (P.chunks > 1 || !render_needs_full(c->ds, P)) P.chunks = std::max(P.chunks, (c->hs->cam.samples + 2047) / 2048);
+    if (pass) {
+      if (render_needs_full(c->ds, P)) { // pixel stream: PixelStats wait in d_pixstate between the passes
+        P.s0 = pass->s0;
+        P.pass_cap = pass->s1;
+        if (!c->d_pixstate) CU(dev_alloc(&c->d_pixstate, (size_t)c->hs->image_width * c->hs->image_height * sizeof(PixState)));
+        P.pixstate = c->d_pixstate;
+      } else { // fixed spp: a window of every pixel's samples on top of the fixed-point sums of the earlier passes
+        P.s0 = pass->s0;
+        P.s_cnt = pass->s1 - pass->s0;
+        P.div_samples = pass->s1;
+        P.keep_accum = 1;
+        P.chunks = std::max(1, std::min(P.chunks, P.s_cnt));
+      }
+    }
     const size_t need_q = 1 + (size_t)P.tiles_x * P.tiles_y * 8; // queue head + one completion counter per 8x4 block
     if (need_q > c->queue_ints) {
       CU(cudaStreamSynchronize(c->stream));
@@ -611,8 +640,8 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       c->queue_ints = need_q;
     }
     // fixed-point radiance sums [H][W][4] u64, only when a pixel's samples are split over CTAs
-    const bool wavefront = c->integrator == RT_INTEGRATOR_WAVEFRONT && !render_needs_full(c->ds, P);
-    const size_t need_s = (P.chunks > 1 || wavefront) ? (size_t)4 * c->hs->image_width * c->hs->image_height : 0;
+    const bool wavefront = c->integrator == RT_INTEGRATOR_WAVEFRONT && !render_needs_full(c->ds, P) && !pass; // passes: megakernel layouts only
+    const size_t need_s = (P.chunks > 1 || wavefront || P.keep_accum) ? (size_t)4 * c->hs->image_width * c->hs->image_height : 0;
     if (need_s > c->scratch_elems) {
       CU(cudaStreamSynchronize(c->stream));
       dev_free(c->d_scratch);
@@ -621,7 +650,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       c->scratch_elems = need_s;
     }
     CU(cudaMemsetAsync(c->d_queue, 0, need_q * sizeof(int), c->stream));
-    if (need_s) {
+    if (need_s && !(pass && !pass->first)) {
       // only the rows of the region are touched
       const size_t row = (size_t)4 * c->hs->image_width;
       CU(cudaMemsetAsync(c->d_scratch + row * P.y0, 0, row * (size_t)(P.y1 - P.y0) * sizeof(unsigned long long), c->stream));
@@ -752,6 +781,81 @@ rt_status rt_camera_render(rt_camera* cam, uint8_t* rgb8, size_t rgb8_len, float
 rt_status rt_camera_render_moments(rt_camera* cam, const rt_region* region, uint8_t* rgb8, size_t rgb8_len,
                                    float* linear_rgb, float* moments, rt_stats* stats) {
   return render_host(cam, region, rgb8, rgb8_len, linear_rgb, moments, stats);
+}
+
+// Progressive render: the same image as rt_camera_render_region, delivered in n_passes growing prefixes of the samples.
+rt_status rt_camera_render_progressive(rt_camera* c, const rt_region* region, uint8_t* rgb8, size_t rgb8_len, float* linear, int32_t n_passes,
+                                       rt_progress_fn on_pass, void* user, rt_stats* stats) {
+  RT_GUARD_BEGIN
+  if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "null camera");
+  if (n_passes < 1) return fail(RT_ERR_INVALID_ARGUMENT, "n_passes must be >= 1");
+  if (c->opts.part_count > 1) return fail(RT_ERR_UNSUPPORTED, "progressive renders are not partitioned");
+  const int W = c->hs->image_width, H = c->hs->image_height;
+  const size_t npx = (size_t)W * H;
+  if (rgb8 && rgb8_len < npx * 3) return fail(RT_ERR_BUFFER_TOO_SMALL, "rgb8 buffer smaller than width*height*3");
+  DeviceGuard g(c->device);
+  RenderParams P0;
+  rt_status st = clip_region(c, region, P0);
+  if (st != RT_OK) return st;
+  if (rgb8 && !c->d_rgb8) CU(dev_alloc(&c->d_rgb8, npx * 3));
+  if (linear && !c->d_linear) CU(dev_alloc(&c->d_linear, npx * 3 * sizeof(float)));
+  const int S = c->hs->cam.samples;
+  const bool stream = c->hs->cam.adaptive || c->hs->cam.mode != 0;
+  const int batch = c->hs->cam.adaptive ? std::max(1, c->hs->cam.a_batch) : 1;
+  rt_stats total;
+  std::memset(&total, 0, sizeof(total));
+  total.samples_min = total.bounces_min = 0x7fffffff;
+  const int rw = P0.x1 - P0.x0, rh = P0.y1 - P0.y0;
+  int prev = 0, passes_run = 0;
+  for (int k = 1; k <= n_passes; ++k) {
+    // prefix of the samples after pass k; the pixel stream stops on batch boundaries only (the convergence check of
+    // camera.ts:348-368 runs there, so a pixel's decisions are those of the one-shot render)
+    long long cap = ((long long)S * k + n_passes - 1) / n_passes;
+    if (k < n_passes) cap = std::min<long long>(S, (cap + batch - 1) / batch * batch);
+    else cap = S;
+    if ((int)cap <= prev && !(S <= 0 && k == n_passes)) continue; // nothing new in this pass (more passes than samples)
+    RenderParams P = P0;
+    P.rgb8 = rgb8 ? c->d_rgb8 : nullptr;
+    P.linear = linear ? c->d_linear : nullptr;
+    const ProgPass pass{prev, (int)cap, passes_run == 0};
+    int launches = 0;
+    CU(cudaEventRecord(c->ev0, c->stream));
+    st = enqueue_render(c, P, nullptr, &launches, (S > 0 && n_passes > 1) ? &pass : nullptr);
+    if (st != RT_OK) return st;
+    CU(cudaEventRecord(c->ev1, c->stream));
+    unsigned long long raw[kStatCount];
+    CU(cudaMemcpyAsync(raw, c->d_stats, sizeof(raw), cudaMemcpyDeviceToHost, c->stream));
+    if (rw > 0 && rh > 0) {
+      const size_t off = (size_t)P0.y0 * W + P0.x0;
+      if (rgb8) CU(cudaMemcpy2DAsync(rgb8 + off * 3, (size_t)W * 3, c->d_rgb8 + off * 3, (size_t)W * 3, (size_t)rw * 3, rh, cudaMemcpyDeviceToHost, c->stream));
+      if (linear) CU(cudaMemcpy2DAsync(linear + off * 3, (size_t)W * 12, c->d_linear + off * 3, (size_t)W * 12, (size_t)rw * 12, rh, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    rt_stats ps;
+    std::memset(&ps, 0, sizeof(ps));
+    unpack_stats(raw, &ps);
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    // RenderStats.merge over the passes: work adds up; a pixel is counted by the pass that completes it
+    total.samples_total += ps.samples_total; total.bounces_total += ps.bounces_total; total.rays += ps.rays;
+    total.node_visits += ps.node_visits; total.prim_tests += ps.prim_tests;
+    total.device_ms += ms; total.kernel_launches += launches;
+    total.bounces_min = std::min(total.bounces_min, ps.bounces_min); total.bounces_max = std::max(total.bounces_max, ps.bounces_max);
+    if (stream) {
+      total.pixels += ps.pixels;
+      total.samples_min = std::min(total.samples_min, ps.samples_min); total.samples_max = std::max(total.samples_max, ps.samples_max);
+    } else { // fixed spp: every pass touches every pixel; all of them have `cap` samples now
+      total.pixels = ps.pixels;
+      total.samples_min = total.samples_max = ps.pixels ? (int32_t)cap : total.samples_min;
+      if (!ps.pixels) total.samples_max = 0;
+    }
+    prev = (int)cap;
+    ++passes_run;
+    if (on_pass && on_pass(user, k, n_passes, (int32_t)cap, &total) != 0) break; // the caller has seen enough
+  }
+  if (stats) *stats = total;
+  return RT_OK;
+  RT_GUARD_END
 }
 
 rt_status rt_camera_trace_primary(rt_camera* c, const rt_region* region, int32_t* obj_id, float* t, float* normal,
@@ -957,6 +1061,7 @@ rt_status rt_multi_render_region(rt_multi* m, const rt_region* region, uint8_t* 
       stats->samples_min = stats->bounces_min = 0x7fffffff;
       for (const rt_stats& s : ps) {
         stats->pixels += s.pixels; stats->samples_total += s.samples_total; stats->bounces_total += s.bounces_total; stats->rays += s.rays;
+        stats->node_visits += s.node_visits; stats->prim_tests += s.prim_tests;
         stats->samples_min = std::min(stats->samples_min, s.samples_min); stats->samples_max = std::max(stats->samples_max, s.samples_max);
         stats->bounces_min = std::min(stats->bounces_min, s.bounces_min); stats->bounces_max = std::max(stats->bounces_max, s.bounces_max);
         stats->device_ms = std::max(stats->device_ms, s.device_ms); stats->kernel_launches += s.kernel_launches;
@@ -1008,6 +1113,7 @@ rt_status rt_multi_render_region(rt_multi* m, const rt_region* region, uint8_t* 
     for (int k = 0; k < n; ++k) {
       const unsigned long long* r = m->h_stats + (size_t)k * kStatCount;
       raw[kStatPixels] += r[kStatPixels]; raw[kStatSamples] += r[kStatSamples]; raw[kStatBounces] += r[kStatBounces]; raw[kStatRays] += r[kStatRays];
+      raw[kStatNodeVisits] += r[kStatNodeVisits]; raw[kStatPrimTests] += r[kStatPrimTests];
       raw[kStatSamplesMin] = std::min(raw[kStatSamplesMin], r[kStatSamplesMin]); raw[kStatSamplesMax] = std::max(raw[kStatSamplesMax], r[kStatSamplesMax]);
       raw[kStatBouncesMin] = std::min(raw[kStatBouncesMin], r[kStatBouncesMin]); raw[kStatBouncesMax] = std::max(raw[kStatBouncesMax], r[kStatBouncesMax]);
       DeviceGuard g(m->cams[k]->device);
@@ -1208,6 +1314,8 @@ __global__ void k_finalize_stats(const unsigned long long* raw, rt_stats* out, i
   s.device_ms = 0;
   s.kernel_launches = launches;
   s.reserved = 0;
+  s.node_visits = raw[kStatNodeVisits];
+  s.prim_tests = raw[kStatPrimTests];
   *out = s;
 }
 cudaError_t launch_finalize_stats(const unsigned long long* raw, rt_stats* out, int launches, cudaStream_t st) {

@@ -101,14 +101,20 @@ RT_DEV ListSmem stage_list(const DevScene& S, ListSmemData& sm) {
 }
 
 template <int KIND, bool LEAF_LOOP = true> // LEAF_LOOP: see leaves_intersect (rt_device.cuh)
-RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
+RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot, WorkCount& wc) {
   RayPre pre = precompute(r, true); // LIST uses idir too (axis-aligned quads); unused parts are dead code
   t = CUDART_INF_F;
   slot = -1;
-  if (KIND == BVH_LIST) trace_list(S, L, r, pre, t, slot);
-  else if (KIND == BVH_SAH) trace_sah<LEAF_LOOP>(S, r, pre, t, slot);
+  ++wc.rays;
+  if (KIND == BVH_LIST) { RT_COUNT_PRIMS(wc, S.n_slots); trace_list(S, L, r, pre, t, slot); }
+  else if (KIND == BVH_SAH) trace_sah<LEAF_LOOP>(S, r, pre, t, slot, wc);
   else trace_ref(S, r, pre, t, slot);
   return slot >= 0;
+}
+template <int KIND, bool LEAF_LOOP = true>
+RT_DEV bool closest_hit(const DevScene& S, const SmemList& L, const Ray& r, float& t, int& slot) {
+  WorkCount wc;
+  return closest_hit<KIND, LEAF_LOOP>(S, L, r, t, slot, wc);
 }
 
 struct PathState {
@@ -223,12 +229,11 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
 // One whole rayColor call on the path's current ray.
 template <int KIND, bool LEAF_LOOP = true>
 RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
-                      unsigned& rays) {
+                      WorkCount& wc) {
   if (path_pre(S.cam, ps, g)) return true;
   float t;
   int slot;
-  ++rays;
-  closest_hit<KIND, LEAF_LOOP>(S, L, ps.ray, t, slot); // world.hit(r, (0.001, inf)) — camera.ts:249
+  closest_hit<KIND, LEAF_LOOP>(S, L, ps.ray, t, slot, wc); // world.hit(r, (0.001, inf)) — camera.ts:249
   return path_post<KIND>(S, &sm, mw, ps, g, t, slot);
 }
 
@@ -249,6 +254,15 @@ RT_DEV void write_pixel(const RenderParams& R, size_t pi, V3 fc) {
 // RenderStats contribution of a lane (renderStats.ts:21-35): warp-reduce, one atomic each.
 // n_pixels pixels were completed, each with pixel_samples samples; n_samples paths were traced.
 // (px_smin, px_smax): fewest / most samples of any pixel this lane completed.
+RT_DEV void flush_work(const RenderParams& R, const WorkCount& wc) { // instrumented build only: executed traversal work
+#ifdef RT_COUNT_EVENTS
+  if (!R.stats) return;
+  const unsigned long long v = warp_sum((unsigned long long)wc.visits), p = warp_sum((unsigned long long)wc.prims);
+  if ((threadIdx.x & 31) == 0 && (v || p)) { atomicAdd(R.stats + kStatNodeVisits, v); atomicAdd(R.stats + kStatPrimTests, p); }
+#else
+  (void)R; (void)wc;
+#endif
+}
 RT_DEV void flush_stats_range(const RenderParams& R, unsigned n_pixels, int px_smin, int px_smax, unsigned n_samples,
                               unsigned bounces_sum, unsigned rays, int min_b, int max_b) {
   if (!R.stats) return;
@@ -306,8 +320,9 @@ RT_DEV bool next_warp_item(const RenderParams& R, int samples, int blocks_per_ro
     it.py0 = (R.y0 / kTile) * kTile + by * 4;
     if (it.px0 >= R.x1 || it.py0 >= R.y1 || it.px0 + 8 <= R.x0 || it.py0 + 4 <= R.y0) continue; // block outside the region
     it.blk = blk;
-    it.s_begin = (int)(((long long)samples * chunk) / chunks);
-    it.s_end = (int)(((long long)samples * (chunk + 1)) / chunks);
+    const int cnt = R.s_cnt > 0 ? R.s_cnt : samples; // progressive pass: a window of the pixel's samples
+    it.s_begin = R.s0 + (int)(((long long)cnt * chunk) / chunks);
+    it.s_end = R.s0 + (int)(((long long)cnt * (chunk + 1)) / chunks);
     return true;
   }
 }
@@ -345,11 +360,12 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
   const int i = it.px0 + (int)(lane & 7u), j = it.py0 + (int)(lane >> 3);
   const bool active = i >= R.x0 && i < R.x1 && j >= R.y0 && j < R.y1;
   const size_t pi = (size_t)j * cam.width + i;
+  const int div = R.div_samples > 0 ? R.div_samples : cam.samples; // progressive pass: samples taken so far
   unsigned wrote = 0;
-  if (R.chunks == 1) {
+  if (R.chunks == 1 && !R.keep_accum) {
     if (active) {
       wrote = 1;
-      write_pixel(R, pi, mk3(from_fixed(sum[0], cam.samples), from_fixed(sum[1], cam.samples), from_fixed(sum[2], cam.samples)));
+      write_pixel(R, pi, mk3(from_fixed(sum[0], div), from_fixed(sum[1], div), from_fixed(sum[2], div)));
     }
   } else {
     if (active) {
@@ -367,7 +383,7 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
       if (active) {
         wrote = 1;
         const unsigned long long* a = R.accum + pi * 4;
-        write_pixel(R, pi, mk3(from_fixed(__ldcg(a), cam.samples), from_fixed(__ldcg(a + 1), cam.samples), from_fixed(__ldcg(a + 2), cam.samples)));
+        write_pixel(R, pi, mk3(from_fixed(__ldcg(a), div), from_fixed(__ldcg(a + 1), div), from_fixed(__ldcg(a + 2), div)));
       }
     }
   }
@@ -398,7 +414,8 @@ k_render_pool(const DevScene S, const RenderParams R) {
   unsigned int* acc = s_acc[POOL ? (threadIdx.x >> 5) : 0];
 
   // RenderStats partials of this lane over all items of its warp
-  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0;
+  WorkCount wc;
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
   WarpItem it;
@@ -446,7 +463,7 @@ k_render_pool(const DevScene S, const RenderParams R) {
         if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
         g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
-        ended = path_step<KIND>(S, L, sm, mw, ps, g, st_rays);
+        ended = path_step<KIND>(S, L, sm, mw, ps, g, wc);
       }
 #ifndef RT_NO_RECONVERGE
       // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
@@ -469,7 +486,8 @@ k_render_pool(const DevScene S, const RenderParams R) {
     st_pixels += item_epilogue(R, cam, it, lane, sum);
     __syncwarp(); // acc is cleared at the top of the next item
   }
-  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, wc.rays, st_bmin, st_bmax);
+  flush_work(R, wc);
 }
 
 // =========================================================================================
@@ -871,7 +889,8 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
   unsigned int* acc = s_acc[threadIdx.x >> 5];
   TravStack stack;
 
-  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0, st_rays = 0;
+  unsigned int st_pixels = 0, st_paths = 0, st_bounces = 0;
+  WorkCount wc;
   int st_bmin = 0x7fffffff, st_bmax = 0;
 
   WarpItem it;
@@ -931,7 +950,8 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
           st_bmax = max(st_bmax, ps.bounces);
           st = ST_NONE;
         } else {
-          ++st_rays;
+          ++wc.rays;
+          RT_COUNT_PRIMS(wc, S.n_unbounded);
           trav_begin(S, ps.ray, tv);
           bp = box_precompute(ps.ray);
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
@@ -971,7 +991,8 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
           int steps = 0;
           TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1 // unrolled copies of the node visit cost more instruction cache than they save
-          while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
+          while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; RT_COUNT_VISIT(wc); }
+          RT_COUNT_LEAVES(wc, lv);
           if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
 #endif
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
@@ -984,7 +1005,8 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
     st_pixels += item_epilogue(R, cam, it, lane, sum);
     __syncwarp();
   }
-  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, st_rays, st_bmin, st_bmax);
+  flush_stats(R, st_pixels, cam.samples, st_paths, st_bounces, wc.rays, st_bmin, st_bmax);
+  flush_work(R, wc);
 }
 
 // =========================================================================================
@@ -1008,6 +1030,20 @@ RT_DEV void moments_add(V3 color, V3 x, int n, float& m2x, float& m2y, float& m2
   m2x = fmaf(x.x - mean_old.x, x.x - mean_new.x, m2x);
   m2y = fmaf(x.y - mean_old.y, x.y - mean_new.y, m2y);
   m2z = fmaf(x.z - mean_old.z, x.z - mean_new.z, m2z);
+}
+
+// pixelConverged (camera.ts:348-368) on the FP64 sums, WITHOUT its two divisions and two square roots:
+//   variance = (s2 - s1^2 / n) / (n - 1),  mean = s1 / n,  converged  <=>  variance <= 0 | NaN  |  1.96 sqrt(variance / n) <= tol mean
+// and for s1 > 0 the last condition is  1.96^2 (n s2 - s1^2) <= tol^2 (n - 1) s1^2  (both sides of the reference's inequality are
+// non-negative, multiply through by n^2 (n - 1) and square); for s1 <= 0 the right-hand side of the reference is <= 0 and only the
+// variance <= 0 branch can hold.  Six FP64 operations instead of ~100 instructions of DDIV / DSQRT sequences: lanes reach their checks
+// at different iterations, so that block used to run in nearly every iteration of the warp's sample loop for one or two lanes.
+RT_DEV bool pixel_converged(double s1, double s2, int samples, float tol) {
+  const double n = (double)samples;
+  const double D = fma(n, s2, -(s1 * s1)); // n (n - 1) variance
+  if (!(D > 0.0)) return true;             // variance <= 0 or NaN (camera.ts:360)
+  const double t2 = (double)tol * (double)tol * (n - 1.0);
+  return s1 > 0.0 && 3.8416 * D <= t2 * (s1 * s1);
 }
 
 // Out of line on purpose: these run once per pixel / per 64 pixels, and the sample loop of k_render_stream is
@@ -1035,6 +1071,22 @@ __device__ __noinline__ void stream_write_pixel(uint8_t* rgb8, float* linear, fl
     m[6] = (float)samples; m[7] = (float)bounces_sum;
   }
 }
+// PixelStats of a pixel between two passes of a progressive render.  Out of line: once per pixel per pass.
+__device__ __noinline__ int pixstate_load(const PixState* ps, size_t pi, float& cx, float& cy, float& cz, double& s1, double& s2, int& samples,
+                                          unsigned& bounces) {
+  const PixState p = ps[pi];
+  cx = p.color[0]; cy = p.color[1]; cz = p.color[2];
+  s1 = p.sum_ill; s2 = p.sum_ill2; samples = p.samples; bounces = p.bounces;
+  return p.done;
+}
+__device__ __noinline__ void pixstate_store(PixState* ps, size_t pi, float cx, float cy, float cz, double s1, double s2, int samples,
+                                            unsigned bounces, int done) {
+  PixState p;
+  p.color[0] = cx; p.color[1] = cy; p.color[2] = cz;
+  p.sum_ill = s1; p.sum_ill2 = s2; p.samples = samples; p.bounces = bounces; p.done = done;
+  ps[pi] = p;
+}
+
 // The warp's pixel stream: lanes named in `want` take the next pixels, in lane order, from the current 8x4 block;
 // when it runs out the next block that belongs to this GPU and touches the region is popped from the queue.
 // Called by the whole warp, only when some lane needs a pixel (rare next to the sample loop).
@@ -1080,8 +1132,11 @@ __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int bl
   return tk;
 }
 
+#ifndef RT_STREAM_LIST_BLOCKS
+#define RT_STREAM_LIST_BLOCKS RT_MIN_BLOCKS
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevScene S, const RenderParams R) {
+__global__ void __launch_bounds__(256, KIND == BVH_LIST ? RT_STREAM_LIST_BLOCKS : RT_MIN_BLOCKS) k_render_stream(const DevScene S, const RenderParams R) {
   __shared__ ListSmemData sm_data;
   const ListSmem sm = stage_list<KIND>(S, sm_data);
   const ListSmem& L = sm;
@@ -1105,17 +1160,25 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
   PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
   Rng g;
   // RenderStats tallies of this lane over all its pixels
-  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0, t_rays = 0;
+  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0;
+  WorkCount wc;
   int t_smin = 0x7fffffff, t_smax = 0, t_bmin = 0x7fffffff, t_bmax = 0;
 
-  auto finish_pixel = [&]() {
+  // progressive pass: the pixel stops at `cap` samples (a multiple of aBatch) and its PixelStats wait in R.pixstate
+  const int cap = R.pass_cap > 0 ? min(R.pass_cap, cam.samples) : cam.samples;
+  int samples0 = 0;
+  unsigned int bounces0 = 0;
+  auto finish_pixel = [&](bool final_) {
     stream_write_pixel(R.rgb8, R.linear, R.moments, cam.width, cam.mode, cam.depth, cam.samples, i, j, samples, bounces_sum, color.x,
                        color.y, color.z, m2x, m2y, m2z);
-    ++t_pixels;
-    t_samples += (unsigned)samples;
-    t_bounces += bounces_sum;
-    t_smin = min(t_smin, samples);
-    t_smax = max(t_smax, samples);
+    if (R.pixstate) pixstate_store(R.pixstate, (size_t)j * cam.width + i, color.x, color.y, color.z, sum_ill, sum_ill2, samples, bounces_sum, final_ ? 1 : 0);
+    if (final_) { // RenderStats.addPixel (renderStats.ts:21-35) once per pixel, when it is complete
+      ++t_pixels;
+      t_smin = min(t_smin, samples);
+      t_smax = max(t_smax, samples);
+    }
+    t_samples += (unsigned)(samples - samples0); // the work of this pass
+    t_bounces += bounces_sum - bounces0;
     have_px = false;
   };
 
@@ -1136,11 +1199,18 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         b_ill = b_ill2 = 0.f;
         countdown = cam.a_batch;
         m2x = m2y = m2z = 0;
+        samples0 = 0; bounces0 = 0;
+        if (R.pixstate && R.s0 > 0) { // a later pass (s0 = the previous cap): pick the pixel up where the last pass left it
+          if (pixstate_load(R.pixstate, (size_t)j * cam.width + i, color.x, color.y, color.z, sum_ill, sum_ill2, samples, bounces_sum)) have_px = false;
+          samples0 = samples; bounces0 = bounces_sum;
+        }
       }
     }
     if (__all_sync(full, !have_px)) break; // stream exhausted and every pixel written
 
     bool stop = have_px && cam.samples <= 0; // while (0 < 0): the pixel gets no sample at all
+    bool final_ = stop;
+    bool ended = false;
     if (have_px && !stop) {
       const uint32_t pixel = (uint32_t)j * (uint32_t)cam.width + (uint32_t)i;
       if (need_path) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
@@ -1149,7 +1219,11 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         ps.ray = camera_ray(cam, i, j, g, true);
         need_path = false;
       }
-      if (path_step<KIND, false>(S, L, sm, mw, ps, g, t_rays)) { // pixel.add(rayColor, bounces, useAdaptiveSampling)
+      ended = path_step<KIND, false>(S, L, sm, mw, ps, g, wc);
+    }
+    __syncwarp(); // every way a path can end meets here: ONE copy of the end-of-sample code (see k_render_pool)
+    {
+      if (ended) { // pixel.add(rayColor, bounces, useAdaptiveSampling)
         color = color + ps.radiance;
         ++samples;
         bounces_sum += (unsigned)ps.bounces;
@@ -1163,7 +1237,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
         if (R.moments) moments_add(color, ps.radiance, samples, m2x, m2y, m2z);
         need_path = true;
         // while (pixel.samples < samples && !pixelConverged(pixel)) — camera.ts:406, evaluated for the next sample
-        stop = samples >= cam.samples;
+        final_ = samples >= cam.samples;
         // the check runs when samples % aBatch == 0 (camera.ts:348-368): a countdown instead of a division per sample
         bool check = false;
         if (cam.adaptive && --countdown == 0) {
@@ -1173,18 +1247,14 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream(const DevS
           b_ill = b_ill2 = 0.f;
           check = samples >= 2;
         }
-        if (!stop && check) {
-          double n = (double)samples;
-          double mean = sum_ill / n;
-          double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
-          if (var <= 0.0 || var != var) stop = true;
-          else stop = 1.96 * sqrt(var) / sqrt(n) <= (double)cam.a_tol * mean;
-        }
+        if (!final_ && check) final_ = pixel_converged(sum_ill, sum_ill2, samples, cam.a_tol);
+        stop = final_ || samples >= cap;
       }
     }
-    if (stop) finish_pixel();
+    if (stop) finish_pixel(final_);
   }
-  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, t_rays, t_bmin, t_bmax);
+  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, wc.rays, t_bmin, t_bmax);
+  flush_work(R, wc);
 }
 
 // =========================================================================================
@@ -1216,17 +1286,24 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
   bool fresh = false;
   Trav tv{-1, 0, CUDART_INF_F, -1};
   BoxPre bp{mk3(0, 0, 0), mk3(0, 0, 0)};
-  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0, t_rays = 0;
+  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0;
+  WorkCount wc;
   int t_smin = 0x7fffffff, t_smax = 0, t_bmin = 0x7fffffff, t_bmax = 0;
 
-  auto finish_pixel = [&]() {
+  const int cap = R.pass_cap > 0 ? min(R.pass_cap, cam.samples) : cam.samples; // progressive pass (see k_render_stream)
+  int samples0 = 0;
+  unsigned int bounces0 = 0;
+  auto finish_pixel = [&](bool final_) {
     stream_write_pixel(R.rgb8, R.linear, R.moments, cam.width, cam.mode, cam.depth, cam.samples, i, j, samples, bounces_sum, color.x,
                        color.y, color.z, m2x, m2y, m2z);
-    ++t_pixels;
-    t_samples += (unsigned)samples;
-    t_bounces += bounces_sum;
-    t_smin = min(t_smin, samples);
-    t_smax = max(t_smax, samples);
+    if (R.pixstate) pixstate_store(R.pixstate, (size_t)j * cam.width + i, color.x, color.y, color.z, sum_ill, sum_ill2, samples, bounces_sum, final_ ? 1 : 0);
+    if (final_) {
+      ++t_pixels;
+      t_smin = min(t_smin, samples);
+      t_smax = max(t_smax, samples);
+    }
+    t_samples += (unsigned)(samples - samples0);
+    t_bounces += bounces_sum - bounces0;
     have_px = false;
   };
   // pixel.add(rayColor, bounces, useAdaptiveSampling) + the loop condition of camera.ts:406 for the next sample
@@ -1242,7 +1319,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
       b_ill2 = fmaf(il, il, b_ill2);
     }
     if (R.moments) moments_add(color, ps.radiance, samples, m2x, m2y, m2z);
-    bool stop = samples >= cam.samples;
+    bool final_ = samples >= cam.samples;
     bool check = false;
     if (cam.adaptive && --countdown == 0) {
       countdown = cam.a_batch;
@@ -1251,14 +1328,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
       b_ill = b_ill2 = 0.f;
       check = samples >= 2;
     }
-    if (!stop && check) { // camera.ts:348-368
-      double n = (double)samples;
-      double mean = sum_ill / n;
-      double var = (sum_ill2 - (sum_ill * sum_ill) / n) / (n - 1.0);
-      if (var <= 0.0 || var != var) stop = true;
-      else stop = 1.96 * sqrt(var) / sqrt(n) <= (double)cam.a_tol * mean;
-    }
-    if (stop) { finish_pixel(); st = ST_NONE; }
+    if (!final_ && check) final_ = pixel_converged(sum_ill, sum_ill2, samples, cam.a_tol); // camera.ts:348-368
+    if (final_ || samples >= cap) { finish_pixel(final_); st = ST_NONE; }
     else { st = ST_BEGIN; fresh = true; }
   };
 
@@ -1278,7 +1349,14 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
         b_ill = b_ill2 = 0.f;
         countdown = cam.a_batch;
         m2x = m2y = m2z = 0;
-        if (cam.samples <= 0) finish_pixel(); // while (0 < 0): the pixel gets no sample at all
+        samples0 = 0; bounces0 = 0;
+        bool skip = false;
+        if (R.pixstate && R.s0 > 0) {
+          skip = pixstate_load(R.pixstate, (size_t)j * cam.width + i, color.x, color.y, color.z, sum_ill, sum_ill2, samples, bounces_sum) != 0;
+          samples0 = samples; bounces0 = bounces_sum;
+        }
+        if (skip) have_px = false;
+        else if (cam.samples <= 0) finish_pixel(true); // while (0 < 0): the pixel gets no sample at all
         else { st = ST_BEGIN; fresh = true; }
       }
     }
@@ -1296,7 +1374,8 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
       if (fresh) { ps.ray = camera_ray(cam, i, j, g, true); fresh = false; }
       if (path_pre(cam, ps, g)) end_sample(); // ended by the depth limit or the roulette: nothing to trace
       else {
-        ++t_rays;
+        ++wc.rays;
+        RT_COUNT_PRIMS(wc, S.n_unbounded);
         trav_begin(S, ps.ray, tv);
         bp = box_precompute(ps.ray);
         st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
@@ -1314,13 +1393,15 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
         int steps = 0;
           TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1
-        while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; }
+        while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; RT_COUNT_VISIT(wc); }
+        RT_COUNT_LEAVES(wc, lv);
         if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
         st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
       }
     }
   }
-  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, t_rays, t_bmin, t_bmax);
+  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, wc.rays, t_bmin, t_bmax);
+  flush_work(R, wc);
 }
 
 // =========================================================================================

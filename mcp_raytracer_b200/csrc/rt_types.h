@@ -148,6 +148,23 @@ struct RenderParams {
   int trav_min_lanes;          // k_render_trav: leave the traversal phase when <= this many lanes still traverse
   int trav_burst;              // k_render_trav: inner-node visits a lane may do between two votes
   int sorted;                  // use k_render_sorted (CTA-wide sort of hits by material class) where it exists
+  // ---- progressive rendering (rt_camera_render_progressive): one launch = one pass ----
+  // fixed spp: this launch renders samples [s0, s0 + s_cnt) of every pixel on top of `accum` (kept from the earlier passes) and
+  // writes the pixel as sum / div_samples; s_cnt == 0: the whole range [0, samples), divisor = samples
+  int s0, s_cnt, div_samples;
+  int keep_accum;              // sums go through `accum` even when chunks == 1
+  // pixel stream (adaptive sampling / modes): a pixel runs until it converges, reaches `samples` or reaches pass_cap samples;
+  // its PixelStats live in pixstate between passes (null: one-shot render)
+  struct PixState* pixstate;
+  int pass_cap;
+};
+// PixelStats of one pixel between two passes of a progressive render (renderStats.ts:67-88)
+struct alignas(8) PixState {
+  float color[3];
+  int samples;
+  double sum_ill, sum_ill2;
+  unsigned int bounces;
+  int done; // converged or all samples taken: later passes skip the pixel
 };
 // ---- wavefront integrator (rt_wavefront.cuh): path pool + queues in HBM ----
 struct U2 { uint32_t x, y; };
@@ -186,7 +203,9 @@ struct WfHost { // device allocations owned by the camera (rt_api.cu)
 
 enum : int {
   kStatPixels = 0, kStatSamples, kStatBounces, kStatRays,
-  kStatSamplesMin, kStatSamplesMax, kStatBouncesMin, kStatBouncesMax, kStatCount
+  kStatSamplesMin, kStatSamplesMax, kStatBouncesMin, kStatBouncesMax,
+  kStatNodeVisits, kStatPrimTests, // instrumented build (-DRT_COUNT_EVENTS) only; 0 otherwise
+  kStatCount
 };
 
 } // namespace rt

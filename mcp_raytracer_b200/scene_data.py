@@ -103,6 +103,8 @@ class rt_stats(C.Structure):
         ("device_ms", C.c_double),
         ("kernel_launches", C.c_int32),
         ("reserved", C.c_int32),
+        ("node_visits", C.c_uint64),
+        ("prim_tests", C.c_uint64),
     ]
 
 

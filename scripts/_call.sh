@@ -1,6 +1,5 @@
 set -x
 cd $GRAFT_REPO_ROOT
-python scripts/gpu_ab.py C2:256,C5:64,C1:1024 base > gpurun_out/r02_ab_c2_4.log 2>&1; cat gpurun_out/r02_ab_c2_4.log
-python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_full_parity.py::test_converged_image_at_baseline_size > gpurun_out/r02_pytest_4.log 2>&1; tail -8 gpurun_out/r02_pytest_4.log
-python scripts/gpu_adaptive.py 1024 1024 C2 2>&1 | tail -5
-ncu --set full --import-source on --clock-control none -k regex:k_render_stream -c 1 -o gpurun_out/r02_c2_adaptive python scripts/prof_render.py C2 256 1 aTolerance=0.05 > gpurun_out/ncu_c2a.log 2>&1; tail -3 gpurun_out/ncu_c2a.log
+for c in 1 2 3 4 6 8 12; do RT_B200_CHUNKS=$c python scripts/prof_render.py C2 1024 3 | sed "s/^/chunks=$c /"; done 2>&1 | tee gpurun_out/r02_c2_chunks.log
+python bench.py --workload C4,C3 --steps 2 --warmup 3 --cpu-seconds 4 > gpurun_out/r02_bench_c4c3.json 2> gpurun_out/r02_bench_c4c3.err; tail -3 gpurun_out/r02_bench_c4c3.err; cut -c1-2500 gpurun_out/r02_bench_c4c3.json
+ncu --set full --import-source on --clock-control none -k regex:k_render_pool -c 1 -o gpurun_out/r02_c2_v3 python scripts/prof_render.py C2 256 1 > gpurun_out/ncu_c2v3.log 2>&1; tail -2 gpurun_out/ncu_c2v3.log

@@ -676,3 +676,64 @@ def test_partition_blocks_follow_rt_block_owner(gpu):
             mask = tile_owner_mask(cam.imageWidth, cam.imageHeight, k, n)
             assert st.pixels == int(mask.sum())
             assert np.all(lin[~mask] == -1.0) and np.all(lin[mask] >= 0.0)
+
+
+# ------------------------------------------------------------------------------------------
+# progressive output (rt_camera_render_progressive): same image, delivered in growing prefixes of the samples
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,opts", [
+    ("C2-cornell", {"width": 96, "samples": 50}),                                         # k_render_pool<LIST>
+    ("C5-layered", {"width": 80, "samples": 24}),                                         # k_render_sorted
+    ("C4-rain", {"width": 96, "samples": 9}),                                             # k_render_trav
+    ("C1-spheres", {"width": 120, "samples": 100, "aTolerance": 0.05, "aBatch": 10}),     # adaptive: k_render_stream<SAH>
+    ("C2-cornell", {"width": 96, "samples": 64, "aTolerance": 0.05, "aBatch": 8}),        # adaptive: k_render_stream<LIST>
+    ("C4-rain", {"width": 96, "samples": 30, "aTolerance": 0.1, "aBatch": 10}),           # adaptive: k_render_stream_trav
+    ("C1-spheres", {"width": 96, "samples": 12, "mode": "bounces"}),                      # render mode through the pixel stream
+])
+def test_progressive_render_ends_in_the_one_shot_image(gpu, name, opts):
+    sd = SCENES[name]()
+    opts = {"aTolerance": 0, "seed": 23, **opts}
+    whole = gpu_render(sd, opts)
+    H, W = whole["rgb8"].shape[:2]
+    ws = whole["stats"]
+    for passes in (1, 4, 7):
+        seen = []
+        with createCameraFromSceneData(sd, opts) as cam:
+            rgb = np.zeros((H, W, 3), np.uint8)
+            lin = np.zeros((H, W, 3), np.float32)
+            first = {}
+
+            def on_pass(k, n, cap, st, rgb=rgb, first=first):
+                seen.append((k, n, cap, st.samples["total"]))
+                if not first:
+                    first["rgb"] = rgb.copy()
+                    first["cap"] = cap
+                return False
+
+            st = cam.renderProgressive(rgb, passes, on_pass, linear=lin)
+        assert np.array_equal(rgb, whole["rgb8"]) and np.array_equal(lin, whole["linear"]), (name, passes)
+        assert (st.pixels, st.samples["total"], st.samples["min"], st.samples["max"]) == (ws.pixels, ws.samples["total"], ws.samples["min"], ws.samples["max"])
+        assert (st.bounces["total"], st.bounces["min"], st.bounces["max"], st.rays) == (ws.bounces["total"], ws.bounces["min"], ws.bounces["max"], ws.rays)
+        caps = [c for _, _, c, _ in seen]
+        assert caps == sorted(set(caps)) and caps[-1] == opts["samples"] and len(seen) <= passes
+        assert [t for *_, t in seen] == sorted(t for *_, t in seen)           # work only ever adds up
+        if passes > 1 and not opts["aTolerance"] and opts.get("mode", "default") == "default" and first["cap"] > 1:
+            # fixed spp: the preview after the first pass IS the render with that many samples (streams keyed by (pixel, sample))
+            assert np.array_equal(first["rgb"], gpu_render(sd, {**opts, "samples": first["cap"]})["rgb8"])
+
+
+def test_progressive_render_can_stop_early_and_refuses_partitions(gpu):
+    sd = SCENES["C2-cornell"]()
+    opts = {"width": 64, "samples": 40, "aTolerance": 0, "seed": 2}
+    with createCameraFromSceneData(sd, opts) as cam:
+        rgb = np.zeros((cam.imageHeight, cam.imageWidth, 3), np.uint8)
+        calls = []
+        st = cam.renderProgressive(rgb, 8, lambda k, n, cap, s: calls.append(cap) or len(calls) == 3)
+        assert len(calls) == 3 and st.samples["max"] == calls[-1] == 15 and st.samples["total"] == st.pixels * 15
+        assert np.array_equal(rgb, gpu_render(sd, {**opts, "samples": 15})["rgb8"])
+        with pytest.raises(RuntimeError, match="boom"):
+            cam.renderProgressive(rgb, 4, lambda *a: (_ for _ in ()).throw(RuntimeError("boom")))
+        assert np.array_equal(gpu_render(sd, opts)["rgb8"], (cam.render(rgb), rgb)[1])   # the camera is still usable
+    with createCameraFromSceneData(sd, {**opts, "partIndex": 0, "partCount": 2}) as cam:
+        with pytest.raises(RaytracerError, match="not partitioned"):
+            cam.renderProgressive(np.zeros((cam.imageHeight, cam.imageWidth, 3), np.uint8), 2)
