@@ -107,6 +107,9 @@ def executed_events(workload, ropts, spp):
         return None
 
 
+ORACLE_BUILD = None
+
+
 def cpu_reference_run(sd, opts, target_seconds, threads):
     """Times the oracle on a BOUNDED sample of the workload that lasts about `target_seconds`: the same
     scene and camera, first at a reduced spp (adaptive sampling is off, so cost is linear in spp) and,
@@ -115,8 +118,15 @@ def cpu_reference_run(sd, opts, target_seconds, threads):
     keeps the whole call bounded even where the reference's own BVH is nearly useless (its per-axis box
     test, aabb.ts:30-59, accepts most boxes along a long ray: 100k-sphere rain scene)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding
     from oracle_binding import OracleCamera
 
+    global ORACLE_BUILD
+    if ORACLE_BUILD is None:  # first use: the host-tuned build (-O3 -march=native, made on this host), else the portable one
+        native = None if os.environ.get("RT_ORACLE_LIB") else oracle_binding.build_native_oracle()
+        if native:
+            os.environ["RT_ORACLE_LIB"] = native
+        ORACLE_BUILD = "-O3 -march=native, built on this host" if (native or os.environ.get("RT_ORACLE_LIB")) else "-O3 (portable build)"
     base = dict(opts)
     full_w, full_spp = int(base["width"]), int(base["samples"])
     # calibration: grow a tiny render until it takes >= 0.2 s (or a hard cap of work is reached)
@@ -289,7 +299,7 @@ def bench_workload(args, workload, rank, world, local_rank, emit, env):
             "config": {"workload": label, "sample": sample},
             "grays_per_s": sum(x["rays"] for x in vals) / sum(x["seconds"] for x in vals) / 1e9,
             "cpu_baseline": {"value": v, "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
-                             "note": "C++ restatement of the TypeScript reference (no node toolchain in the image); row strips, one per thread, like src/raytracer.ts:60-90"},
+                             "note": f"C++ restatement of the TypeScript reference (no node toolchain in the image), {ORACLE_BUILD}; row strips, one per thread, like src/raytracer.ts:60-90"},
             "e2e": {"value": v, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
@@ -472,7 +482,7 @@ def bench_workload(args, workload, rank, world, local_rank, emit, env):
         if world == 1:
             cpu = {"value": c["mpaths_per_s"], "unit": "Mpaths/s", "cores": cpu_threads, "kind": "port", "sample": sample,
                    "grays_per_s": c["grays_per_s"], "seconds": c["seconds"],
-                   "note": "C++ restatement of the TypeScript reference (cannot run here); row strips, one per thread, like src/raytracer.ts:60-90"}
+                   "note": f"C++ restatement of the TypeScript reference (cannot run here), {ORACLE_BUILD}; row strips, one per thread, like src/raytracer.ts:60-90"}
         flops_per_path = algorithmic_flops(c["counters"], c["n_lights"], float(sd["camera"].get("aperture", 0))) / max(1, c["counters"]["paths"])
         kernel_s = (total_ms * 1e-3) / args.steps  # one render kernel per step (max over ranks)
         achieved = flops_per_path * paths_per_step / kernel_s / 1e12

@@ -603,15 +603,21 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
   *launches = 0;
   if (P.x1 > P.x0 && P.y1 > P.y0) {
     render_tile_grid(P, &P.tiles_x, &P.tiles_y);
+    if (P.part_count > 1) { // runs of part_count consecutive blocks (whole-image numbering) that overlap the region's block rows
+      const long long bpr = (c->hs->image_width + 7) / 8;
+      const long long i0 = (long long)(P.y0 / 4) * bpr, i1 = (long long)((P.y1 - 1) / 4 + 1) * bpr;
+      P.run0 = (int)(i0 / P.part_count);
+      P.n_runs = (int)((i1 - 1) / P.part_count) - P.run0 + 1;
+    }
     if (render_needs_full(c->ds, P)) P.chunks = 1;
     else if (c->chunks > 0) P.chunks = std::min(c->chunks, std::max(1, c->hs->cam.samples)); // never an empty chunk (k_render_sorted skips them)
     else {
       // Sample chunks per pixel: enough (8x4 block, chunk) warp items that the blocks this GPU owns
-      // keep it busy for >= 16 rounds of resident warps, so the tail of the render stays ~1/32 of it
+      // keep it busy for >= 20 rounds of resident warps (3 CTAs x 8 warps per SM), so the tail of the render stays ~1/40 of it
       // whether the GPU renders the whole image or 1/8 of it.  Sums are exact fixed point, so the
       // image does not depend on this choice.  A chunk stays <= 2048 samples (limb accumulators).
       const long long owned = std::max(1LL, (long long)P.tiles_x * P.tiles_y * 8 / std::max(1, P.part_count));
-      const long long target = 16LL * c->sms * 2 * 8;
+      const long long target = 20LL * c->sms * 3 * 8; // (Cornell 1024^2 @1024, one GPU: chunks 1 / 2 / 3 / 4 / 8 = 114.8 / 108.5 / 107.7 / 108.0 / 109.5 ms)
       long long k = (target + owned - 1) / owned;
       k = std::min<long long>(k, std::max(1, c->hs->cam.samples / 16));
       P.chunks = (int)std::min<long long>(std::max<long long>(k, 1), 64);
@@ -631,7 +637,7 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
         P.chunks = std::max(1, std::min(P.chunks, P.s_cnt));
       }
     }
-    const size_t need_q = 1 + (size_t)P.tiles_x * P.tiles_y * 8; // queue head + one completion counter per 8x4 block
+    const size_t need_q = 1 + std::max((size_t)P.tiles_x * P.tiles_y * 8, (size_t)P.n_runs); // queue head + one completion counter per 8x4 block / run
     if (need_q > c->queue_ints) {
       CU(cudaStreamSynchronize(c->stream));
       dev_free(c->d_queue);

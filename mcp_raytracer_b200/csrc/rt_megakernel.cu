@@ -302,22 +302,30 @@ RT_DEV float from_fixed(unsigned long long s, int samples) { return (float)(((do
 struct WarpItem {
   int blk, px0, py0, s_begin, s_end;
 };
-// Pops items until one belongs to this GPU and touches the region.  False = queue exhausted.
+// Pops items until one touches the region.  False = queue exhausted.
+// One GPU: items = (block of the region's tile grid, chunk).  Several GPUs: items = (run of part_count consecutive blocks,
+// chunk) and the block is the ONE this part owns in that run (owned_block_of_run) — a GPU never pops another GPU's work
+// (round 1 popped every block of the image and skipped 7 of 8: at 8 GPUs that was 166 dependent atomics per warp, most of
+// the ~0.8 ms each GPU lost against the ideal eighth of the one-GPU time).
 RT_DEV bool next_warp_item(const RenderParams& R, int samples, int blocks_per_row, unsigned lane, WarpItem& it) {
   const int chunks = R.chunks;
   const int blocks_x = R.tiles_x * 2, blocks_y = R.tiles_y * 4; // 8x4 blocks covering the tile grid
-  const int n_items = blocks_x * blocks_y * chunks;
+  const int n_items = (R.part_count > 1 ? R.n_runs : blocks_x * blocks_y) * chunks;
   for (;;) {
     int item = 0;
     if (lane == 0) item = atomicAdd(R.queue, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) return false;
     const int blk = item / chunks, chunk = item - blk * chunks;
-    const int bx = blk % blocks_x, by = blk / blocks_x;
-    if (R.part_count > 1 && block_owner((R.x0 / kTile) * 2 + bx, (R.y0 / kTile) * 4 + by, blocks_per_row, R.part_count) != R.part_index)
-      continue; // another GPU's block
-    it.px0 = (R.x0 / kTile) * kTile + bx * 8;
-    it.py0 = (R.y0 / kTile) * kTile + by * 4;
+    if (R.part_count > 1) {
+      const unsigned i = owned_block_of_run((unsigned)(R.run0 + blk), R.part_index, R.part_count);
+      it.px0 = (int)(i % (unsigned)blocks_per_row) * 8;
+      it.py0 = (int)(i / (unsigned)blocks_per_row) * 4;
+    } else {
+      const int bx = blk % blocks_x, by = blk / blocks_x;
+      it.px0 = (R.x0 / kTile) * kTile + bx * 8;
+      it.py0 = (R.y0 / kTile) * kTile + by * 4;
+    }
     if (it.px0 >= R.x1 || it.py0 >= R.y1 || it.px0 + 8 <= R.x0 || it.py0 + 4 <= R.y0) continue; // block outside the region
     it.blk = blk;
     const int cnt = R.s_cnt > 0 ? R.s_cnt : samples; // progressive pass: a window of the pixel's samples
@@ -973,28 +981,12 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
           if (__any_sync(0xffffffffu, st == ST_HIT || st == ST_BEGIN || (st == ST_NONE && !retired))) break;
         }
         if (st == ST_TRACE) {
-#ifdef RT_TRAV_SPEC
-          // speculative while-while: a lane that already holds leaves walks on (its second leaf set) for as long as
-          // some lane of the warp still searches its first leaf — it would sit idle in those steps otherwise
-          TravLeaves lv{0, 0, 0, 0}, lw{0, 0, 0, 0};
-#pragma unroll 1
-          for (int steps = 0; steps < R.trav_burst; ++steps) {
-            if (!__any_sync(tt, tv.cur >= 0 && lv.a == 0)) break;
-            if (tv.cur >= 0 && (lv.a == 0 || lw.a == 0)) {
-              TravLeaves nw{0, 0, 0, 0};
-              trav_inner(S, bp, tv, stack, nw);
-              if (lv.a == 0) lv = nw; else lw = nw;
-            }
-          }
-          if (lv.a != 0) trav_leaves2(S, ps.ray, bp, tv, lv, lw);
-#else
           int steps = 0;
           TravLeaves lv{0, 0, 0, 0};
 #pragma unroll 1 // unrolled copies of the node visit cost more instruction cache than they save
           while (tv.cur >= 0 && lv.a == 0 && steps < R.trav_burst) { trav_inner(S, bp, tv, stack, lv); ++steps; RT_COUNT_VISIT(wc); }
           RT_COUNT_LEAVES(wc, lv);
           if (lv.a != 0) trav_leaves(S, ps.ray, bp, tv, lv);
-#endif
           st = tv.cur >= 0 ? ST_TRACE : ST_HIT;
         }
       }
@@ -1097,7 +1089,7 @@ struct StreamTake {
 };
 __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int blk_x0, int blk_y0, bool queue_empty, int* queue,
                                                int n_items, int tiles_x, int rx0, int ry0, int rx1, int ry1, int part_index, int part_count,
-                                               int blocks_per_row, unsigned lane) {
+                                               int run0, int blocks_per_row, unsigned lane) {
   StreamTake tk{0, 0, 0, cursor, blk_x0, blk_y0, queue_empty ? 1 : 0};
   const unsigned lt_mask = (1u << lane) - 1u, full = 0xffffffffu;
   bool mine = (want >> lane) & 1u;
@@ -1110,10 +1102,17 @@ __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int bl
         if (lane == 0) item = atomicAdd(queue, 1);
         item = __shfl_sync(full, item, 0);
         if (item >= n_items) { tk.queue_empty = 1; break; }
-        const int tile = item >> 3, sub = item & 7;
-        const int tx = (rx0 / kTile) + tile % tiles_x, ty = (ry0 / kTile) + tile / tiles_x;
-        if (part_count > 1 && block_owner(tx * 2 + (sub & 1), ty * 4 + (sub >> 1), blocks_per_row, part_count) != part_index) continue; // another GPU's block
-        const int bx = tx * kTile + (sub & 1) * 8, by = ty * kTile + (sub >> 1) * 4;
+        int bx, by;
+        if (part_count > 1) { // item = a run of part_count blocks: the one block this part owns in it
+          const unsigned i = owned_block_of_run((unsigned)(run0 + item), part_index, part_count);
+          bx = (int)(i % (unsigned)blocks_per_row) * 8;
+          by = (int)(i / (unsigned)blocks_per_row) * 4;
+        } else {
+          const int tile = item >> 3, sub = item & 7;
+          const int tx = (rx0 / kTile) + tile % tiles_x, ty = (ry0 / kTile) + tile / tiles_x;
+          bx = tx * kTile + (sub & 1) * 8;
+          by = ty * kTile + (sub >> 1) * 4;
+        }
         if (bx >= rx1 || by >= ry1 || bx + 8 <= rx0 || by + 4 <= ry0) continue;
         tk.blk_x0 = bx; tk.blk_y0 = by; tk.cursor = 0;
         found = true;
@@ -1143,7 +1142,7 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? RT_STREAM_LIST_BLOCKS 
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
-  const int n_items = R.tiles_x * R.tiles_y * 8; // 8x4 blocks, eight per 16x16 tile
+  const int n_items = R.part_count > 1 ? R.n_runs : R.tiles_x * R.tiles_y * 8; // 8x4 blocks, eight per 16x16 tile | one owned block per run
 
   // the warp's stream (warp-uniform)
   int blk_x0 = 0, blk_y0 = 0, cursor = 32;
@@ -1187,7 +1186,7 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? RT_STREAM_LIST_BLOCKS 
     const unsigned want = __ballot_sync(full, !have_px);
     if (want != 0u) {
       const StreamTake tk = stream_take(want, cursor, blk_x0, blk_y0, queue_empty, R.queue, n_items, R.tiles_x, R.x0, R.y0, R.x1,
-                                        R.y1, R.part_index, R.part_count, (cam.width + 7) >> 3, lane);
+                                        R.y1, R.part_index, R.part_count, R.run0, (cam.width + 7) >> 3, lane);
       cursor = tk.cursor; blk_x0 = tk.blk_x0; blk_y0 = tk.blk_y0; queue_empty = tk.queue_empty != 0;
       if (tk.got) {
         i = tk.i; j = tk.j;
@@ -1267,7 +1266,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
   const DevCamera& cam = S.cam;
   const MixW mw = make_mixw(S);
   const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu;
-  const int n_items = R.tiles_x * R.tiles_y * 8; // 8x4 blocks, eight per 16x16 tile
+  const int n_items = R.part_count > 1 ? R.n_runs : R.tiles_x * R.tiles_y * 8; // 8x4 blocks, eight per 16x16 tile | one owned block per run
   TravStack stack;
 
   int blk_x0 = 0, blk_y0 = 0, cursor = 32; // the warp's pixel stream (warp-uniform)
@@ -1338,7 +1337,7 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
     const unsigned want = __ballot_sync(full, st == ST_NONE && !have_px);
     if (want != 0u) {
       const StreamTake tk = stream_take(want, cursor, blk_x0, blk_y0, queue_empty, R.queue, n_items, R.tiles_x, R.x0, R.y0, R.x1,
-                                        R.y1, R.part_index, R.part_count, (cam.width + 7) >> 3, lane);
+                                        R.y1, R.part_index, R.part_count, R.run0, (cam.width + 7) >> 3, lane);
       cursor = tk.cursor; blk_x0 = tk.blk_x0; blk_y0 = tk.blk_y0; queue_empty = tk.queue_empty != 0;
       if (tk.got) {
         i = tk.i; j = tk.j;
@@ -1532,7 +1531,12 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   const bool sorted_list = (env_sorted || R.sorted) && S.cam.samples > 0;
   switch (S.bvh_kind) {
     case BVH_LIST:
-      if (pool_list) return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st, RT_LIST_THREADS);
+      // Lane-keeps-pixel (POOL = false) has no queue arithmetic but its lanes finish an item at different times; with short
+      // items (a GPU that owns 1/8 of the blocks cuts its pixels' samples into ~18 chunks to keep 20 rounds of warps busy)
+      // that intra-warp tail costs more than the pair queue.  Cornell 1024 spp, bit-identical images: whole image, 341
+      // samples per item: 107.1 vs 107.8 ms; one part of eight, 57 samples per item: 14.35 vs 13.87 ms (ideal 13.39).
+      if (pool_list || (R.s_cnt > 0 ? R.s_cnt : S.cam.samples) / (R.chunks > 0 ? R.chunks : 1) < 128)
+        return launch_persistent(k_render_pool<BVH_LIST, true>, S, R, work, sms, st, RT_LIST_THREADS);
 #ifdef RT_EXPERIMENTAL_WQ
       {
         static const int wq = getenv("RT_B200_WQ") ? atoi(getenv("RT_B200_WQ")) : 0;

@@ -127,10 +127,19 @@ RT_HD inline int block_owner(int bx, int by, int blocks_per_row, int n) {
   return (int)((r + h) % (unsigned)n);
 }
 
+// The block part `part` owns in run g (inverse of block_owner): linear index over the whole image.
+RT_HD inline unsigned owned_block_of_run(unsigned g, int part, int n) {
+  unsigned h = g * 0x9E3779B1u;
+  h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13;
+  const unsigned r = ((unsigned)part + (unsigned)n - h % (unsigned)n) % (unsigned)n;
+  return g * (unsigned)n + r;
+}
+
 // Per-render launch parameters.
 struct RenderParams {
   int x0, y0, x1, y1;          // region, clipped to the image
   int part_index, part_count;  // this GPU renders the 8x4 blocks with block_owner(...) == part_index
+  int run0, n_runs;            // part_count > 1: the runs of part_count consecutive blocks that overlap the region's block rows
   uint8_t* rgb8;               // [H][W][3] or null
   float* linear;               // [H][W][3] or null
   float* moments;              // [H][W][8] or null

@@ -38,10 +38,22 @@ def build_oracle() -> str:
     return so
 
 
+def build_native_oracle() -> Optional[str]:
+    """`make native`: the oracle compiled with -march=native ON THIS HOST (bench.py's CPU baseline).
+    None when there is no compiler here or the build fails; the portable build is used then."""
+    d = os.path.join(ROOT, "oracle")
+    try:
+        subprocess.check_call(["make", "-C", d, "native"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=300)
+    except Exception:
+        return None
+    so = os.path.join(d, "_native", "liboracle.so")
+    return so if os.path.exists(so) else None
+
+
 def lib() -> C.CDLL:
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build_oracle())
+        L = C.CDLL(os.environ.get("RT_ORACLE_LIB") or build_oracle())
         dp = C.POINTER(C.c_double)
         fp = C.POINTER(C.c_float)
         L.orc_last_error.restype = C.c_char_p
