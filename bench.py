@@ -214,9 +214,9 @@ class ClockSampler:
 
 def measured_traffic(workload, world, overridden):
     """dram__bytes_read.sum + dram__bytes_write.sum of the render kernel, per launch, from the committed
-    `ncu --set full` capture of this command (profiles/r01_bench_traffic.json); None when the run is not that one."""
+    `ncu --set full` capture of this command (profiles/r02_bench_traffic.json); None when the run is not that one."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_traffic.json")))
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_bench_traffic.json")))
     except Exception:
         return None
     if overridden or t.get("workload") != workload or t.get("n_gpus") != world:

@@ -1081,7 +1081,7 @@ rt_status rt_multi_render_region(rt_multi* m, const rt_region* region, uint8_t* 
     if (rgb8 && !m->d_rgb8) CU(dev_alloc(&m->d_rgb8, npx * 3));
     if (linear && !m->d_linear) CU(dev_alloc(&m->d_linear, npx * 3 * sizeof(float)));
   }
-  RenderParams P0;
+  RenderParams P0{};
   int launches_total = 0;
   for (int k = 0; k < n; ++k) {
     rt_camera* c = m->cams[k];

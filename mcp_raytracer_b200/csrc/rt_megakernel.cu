@@ -1565,6 +1565,10 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
       }
       static const bool trav_always = getenv("RT_B200_TRAV_ALWAYS") != nullptr;
       if (!trav_always && (no_trav || S.n_nodes < kTravNodes)) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
+      // (Measured and removed, round 2: TWO paths per lane — the active one in registers, the other parked in shared memory,
+      //  swapped in when the active ray finishes so the lane keeps traversing; bit-identical image, 100 k spheres at 32 spp
+      //  390 -> 417-436 ms over every min-lanes / burst setting: the swaps, the second service pass and the second traversal
+      //  stack cost more than the idle lanes they fill.)
       return launch_persistent(k_render_trav, S, R, work, sms, st, RT_TRAV_THREADS);
     default: return launch_persistent(k_render_pool<BVH_REFERENCE, true>, S, R, work, sms, st);
   }

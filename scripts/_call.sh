@@ -1,4 +1,6 @@
 cd $GRAFT_REPO_ROOT
-for c in 4 8 12 18 32 64; do echo -n "chunks=$c "; RT_B200_CHUNKS=$c python scripts/prof_render.py C2 1024 4 partIndex=3 partCount=8 2>&1 | tail -1; done
-for c in 4 8 18 32 64; do echo -n "POOL chunks=$c "; RT_B200_POOL_LIST=1 RT_B200_CHUNKS=$c python scripts/prof_render.py C2 1024 4 partIndex=3 partCount=8 2>&1 | tail -1; done
-for c in 2 3 4; do echo -n "POOL whole chunks=$c "; RT_B200_POOL_LIST=1 RT_B200_CHUNKS=$c python scripts/prof_render.py C2 1024 4 2>&1 | tail -1; done
+python scripts/gpu_ab.py C4:32 base 2>&1 | tail -1
+RT_B200_TRAV2=1 python scripts/gpu_ab.py C4:32 base 2>&1 | tail -1
+for m in 4 8 12 16 20; do echo -n "trav2 min=$m "; RT_B200_TRAV2=1 RT_B200_TRAV_MIN=$m python scripts/gpu_ab.py C4:32 base 2>&1 | tail -1; done
+for b in 2 6 8; do echo -n "trav2 burst=$b "; RT_B200_TRAV2=1 RT_B200_TRAV_BURST=$b python scripts/gpu_ab.py C4:32 base 2>&1 | tail -1; done
+RT_B200_TRAV2=1 python -m pytest tests -m gpu -q -x -k "deep_tree or C4 or rain or progressive" 2>&1 | tail -3
