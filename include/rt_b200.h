@@ -83,6 +83,17 @@ enum { RT_BVH_AUTO = 0, RT_BVH_REFERENCE = 1, RT_BVH_SAH = 2, RT_BVH_LIST = 3 };
  * scene has Mixed/Layered materials, else MEGAKERNEL. */
 enum { RT_INTEGRATOR_AUTO = 0, RT_INTEGRATOR_MEGAKERNEL = 1, RT_INTEGRATOR_WAVEFRONT = 2, RT_INTEGRATOR_SORTED = 3 };
 
+/* How the direct light of the listed lights (SceneObject.light, src/scenes/scenes.ts:74-79) is estimated at a diffuse
+ * bounce.  MIXTURE = the reference's estimator: ONE scattered ray drawn from 0.5 cosine + 0.5 light pdf
+ * (src/camera.ts:285-315, src/geometry/pdf.ts:57-99); the parity configuration and the default.
+ * SHADOW_RAYS = next-event estimation: a shadow ray towards a point drawn on a listed light carries that light's
+ * emission (weighted by cos / (pi * light pdf), visibility = the closest hit along it is a listed light), the path
+ * continues on a cosine-distributed ray, and a listed light met by that ray adds no emission (it was counted by the
+ * shadow ray).  Same expectation per pixel — the converged image is the reference's — at lower variance per sample
+ * when lights are small; NOT the same sample values, so same-seed comparisons with the reference estimator do not
+ * apply.  Runs in the pixel-stream kernels for every tree kind, adaptive or fixed spp, all modes. */
+enum { RT_LIGHTS_MIXTURE = 0, RT_LIGHTS_SHADOW_RAYS = 1 };
+
 /* CameraData — src/scenes/sceneData.ts:22-37; defaults src/camera.ts:62-71 */
 typedef struct rt_camera_desc {
   double vfov;
@@ -138,6 +149,7 @@ typedef struct rt_render_opts {
    * mcp_raytracer_b200/distributed.py).  Only owned pixels are rendered / written. */
   int32_t part_index;     /* 0 <= part_index < part_count */
   int32_t part_count;     /* <= 1 means the whole region */
+  int32_t light_sampling; /* RT_LIGHTS_* */
 } rt_render_opts;
 
 /* RenderRegion — src/camera.ts:54-59 */

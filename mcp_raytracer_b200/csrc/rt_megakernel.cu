@@ -121,6 +121,7 @@ struct PathState {
   Ray ray;
   V3 tp, radiance;
   int bounces;
+  float listed_w; // shadow-ray estimator only: weight of a LISTED light's emission met by ps.ray (1, or the scattered ray's MIS weight)
 };
 
 // rayColor, part 1 (camera.ts:228-245): depth limit and Russian roulette.  True = the path ended.
@@ -235,6 +236,112 @@ RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, 
   int slot;
   closest_hit<KIND, LEAF_LOOP>(S, L, ps.ray, t, slot, wc); // world.hit(r, (0.001, inf)) — camera.ts:249
   return path_post<KIND>(S, &sm, mw, ps, g, t, slot);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RT_LIGHTS_SHADOW_RAYS — rayColor with next-event estimation instead of the reference's one-sample mixture (rt_b200.h).
+// At a diffuse scatter the reference draws ONE direction from 0.5 cosine + 0.5 p_light and follows it.  Here the two
+// halves become two rays: a shadow ray along a direction drawn from p_light (the light list's own generators and pdfs,
+// pdf.ts:57-99 / quad.ts / sphere.ts) answers "which listed light does this direction meet first" and carries that
+// light's emission; the scattered ray is cosine-distributed and carries everything else.  Where the scattered ray itself
+// meets a listed light both rays estimate the same emission, and the two estimates are combined with the balance
+// heuristic (weights p_light / (p_light + p_cos) and p_cos / (p_light + p_cos)): next-event estimation alone has a
+// 1/d^2 singularity next to a light (the ceiling around the Cornell light, 0.01 above it) that the reference's mixture
+// does not have.  Each part is unbiased, the weights sum to 1: the pixel's expectation is the reference's
+// (tests/test_gpu_shadow_rays.py compares converged images with the oracle's mixture estimator).  Depth limit,
+// roulette, bounce counting, specular scatter and the pdf <= 1e-4 cut of camera.ts:298-301 are the reference's.
+// ---------------------------------------------------------------------------------------------------
+RT_DEV bool is_listed_light(const DevScene& S, int slot) {
+  bool listed = false;
+  for (int k = 0; k < S.n_lights; ++k) listed |= S.lights[k].slot == slot;
+  return listed;
+}
+RT_DEV float light_list_pdf(const DevScene& S, const MixW& mw, V3 p, V3 dir) { // HittableListPDF.value, pdf.ts:74-86
+  float sum = 0.f;
+  for (int k = 0; k < mw.nl; ++k) sum += light_pdf_value(S, S.lights[k], p, dir);
+  return sum / (float)mw.nl;
+}
+template <int KIND>
+RT_DEV bool path_post_shadow(const DevScene& S, const SmemList& L, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t,
+                             int slot, WorkCount& wc) {
+  const DevCamera& cam = S.cam;
+  if (slot < 0) { // camera.ts:252-258
+    V3 ud = normalize3(ps.ray.d);
+    float a = 0.5f * (ud.y + 1.0f);
+    V3 bg = ld3(cam.bg_top) * (1.0f - a) + ld3(cam.bg_bottom) * a;
+    ps.radiance = ps.radiance + bg * ps.tp;
+    return true;
+  }
+  int type, root;
+  F4 p0;
+  if (KIND == BVH_LIST) { type = sm->type(slot); root = sm->mat(slot); p0 = sm->p0(slot); }
+  else { I2 info = ldgi2(S.slot_info + slot); type = (info.y >> 30) & 3; root = info.x; p0 = ldg4(S.p0 + slot); }
+  const Surf sf = surface_at(type, p0, ps.ray, t);
+  const I4 mb = ldgi4(S.matB + root);
+  const F4 ma = ldg4(S.matA + root);
+  if (mb.w) { // emitted * throughput (camera.ts:261); a listed light met by a scattered ray shares it with the shadow ray
+    F4 e = ldg4(S.matE + root);
+    const float w = ps.listed_w < 1.f && is_listed_light(S, slot) ? ps.listed_w : 1.f;
+    ps.radiance = ps.radiance + xyz(e) * ps.tp * w;
+  }
+  Scatter sc;
+  if (mb.x == MAT_LAMBERT) { sc.kind = SCATTER_DIFFUSE; sc.attenuation = xyz(ma); sc.dir = mk3(0, 0, 0); }
+  else if (mb.x == MAT_LIGHT) return true;
+  else sc = scatter_material(S, root, mb, ma, ps.ray.d, sf, g);
+  if (sc.kind == SCATTER_NONE) return true;
+  ++ps.bounces;
+  ps.listed_w = 1.f;
+  if (sc.kind == SCATTER_SPECULAR) {
+    ps.tp = ps.tp * sc.attenuation;
+    ps.ray = Ray{sf.p, sc.dir};
+    return false;
+  }
+  const Onb onb = make_onb<true>(sf.n);
+  const float kInvPi = 0.31830988618f;
+  if (mw.nl > 0) {
+    // ---- the shadow ray: one listed light chosen uniformly (pdf.ts:88-99 picks its generator the same way) ----
+    const float u_sel = g.next(), r1 = g.next(), r2 = g.next();
+    const int chosen = min((int)(u_sel * (float)mw.nl), mw.nl - 1);
+    const V3 ldir = light_random_vec(S.lights[chosen], sf.p, r1, r2);
+    const float p_cos = dot3(ldir, onb.w) * kInvPi;
+    const float p_light = light_list_pdf(S, mw, sf.p, ldir);
+    if (p_cos > 0.f && p_light > 0.0001f) { // (NaN pdfs — a sphere light seen from inside — fail the comparison)
+      float ts;
+      int ss;
+      closest_hit<KIND, false>(S, L, Ray{sf.p, ldir}, ts, ss, wc);
+      if (ss >= 0 && is_listed_light(S, ss)) {
+        int root_l;
+        if (KIND == BVH_LIST) root_l = sm->mat(ss);
+        else root_l = ldgi2(S.slot_info + ss).x;
+        if (ldgi4(S.matB + root_l).w) {
+          const F4 e = ldg4(S.matE + root_l);
+          // f / p_light * w_light = (albedo p_cos) / (p_light + p_cos)
+          ps.radiance = ps.radiance + xyz(e) * (ps.tp * sc.attenuation) * (p_cos * rcp_approx(p_light + p_cos));
+        }
+      }
+    }
+  }
+  // ---- the scattered ray: cosine-distributed, pdf = scatter pdf, so the weight is the albedo ----
+  const float r3 = g.next(), r4 = g.next();
+  const V3 dir = onb_local(onb, cosine_direction(r3, r4));
+  const float p_cos2 = dot3(dir, onb.w) * kInvPi;
+  if (!(p_cos2 > 0.0001f)) return true; // camera.ts:298-301
+  if (mw.nl > 0) {
+    const float p_light2 = light_list_pdf(S, mw, sf.p, dir);
+    ps.listed_w = p_light2 > 0.0001f ? p_cos2 * rcp_approx(p_light2 + p_cos2) : 1.f; // the shadow ray never takes a direction of pdf <= 1e-4
+  }
+  ps.tp = ps.tp * sc.attenuation;
+  ps.ray = Ray{sf.p, dir};
+  return false;
+}
+template <int KIND>
+RT_DEV bool path_step_shadow(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
+                             WorkCount& wc) {
+  if (path_pre(S.cam, ps, g)) return true;
+  float t;
+  int slot;
+  closest_hit<KIND, false>(S, L, ps.ray, t, slot, wc);
+  return path_post_shadow<KIND>(S, L, &sm, mw, ps, g, t, slot, wc);
 }
 
 // finalColor (camera.ts:326-340, default mode) + writeColorToBuffer (camera.ts:455-472)
@@ -1134,7 +1241,7 @@ __device__ __noinline__ StreamTake stream_take(unsigned want, int cursor, int bl
 #ifndef RT_STREAM_LIST_BLOCKS
 #define RT_STREAM_LIST_BLOCKS RT_MIN_BLOCKS
 #endif
-template <int KIND>
+template <int KIND, bool SHADOW = false> // SHADOW: the shadow-ray estimator (path_post_shadow)
 __global__ void __launch_bounds__(256, KIND == BVH_LIST ? RT_STREAM_LIST_BLOCKS : RT_MIN_BLOCKS) k_render_stream(const DevScene S, const RenderParams R) {
   __shared__ ListSmemData sm_data;
   const ListSmem sm = stage_list<KIND>(S, sm_data);
@@ -1212,13 +1319,13 @@ __global__ void __launch_bounds__(256, KIND == BVH_LIST ? RT_STREAM_LIST_BLOCKS 
     bool ended = false;
     if (have_px && !stop) {
       const uint32_t pixel = (uint32_t)j * (uint32_t)cam.width + (uint32_t)i;
-      if (need_path) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
+      if (need_path) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; ps.listed_w = 1.f; }
       g.begin(pixel, (uint32_t)samples, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi);
       if (need_path) {
         ps.ray = camera_ray(cam, i, j, g, true);
         need_path = false;
       }
-      ended = path_step<KIND, false>(S, L, sm, mw, ps, g, wc);
+      ended = SHADOW ? path_step_shadow<KIND>(S, L, sm, mw, ps, g, wc) : path_step<KIND, false>(S, L, sm, mw, ps, g, wc);
     }
     __syncwarp(); // every way a path can end meets here: ONE copy of the end-of-sample code (see k_render_pool)
     {
@@ -1463,7 +1570,7 @@ void render_tile_grid(const RenderParams& R, int* tiles_x, int* tiles_y) {
 
 bool render_needs_full(const DevScene& S, const RenderParams& R) {
   static const bool force = getenv("RT_B200_FORCE_PIXELS") != nullptr; // development switch
-  return force || S.cam.adaptive || S.cam.mode != 0 || R.moments != nullptr;
+  return force || S.cam.adaptive || S.cam.mode != 0 || R.moments != nullptr || S.cam.shadow_rays;
 }
 
 // ctas_of_work counts 256-thread CTAs (eight warp items each); kernels with another CTA size scale it.
@@ -1513,6 +1620,13 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   constexpr int kTravNodes = 16384; // tree size from which resumable traversal beats the whole-query walk (see case BVH_SAH below)
   if (render_needs_full(S, R)) {
     static const bool no_stream_trav = getenv("RT_B200_NO_STREAM_TRAV") != nullptr; // development switch
+    if (S.cam.shadow_rays) { // whole-query walks for every tree size: the shadow ray is traced inside the shading step
+      switch (S.bvh_kind) {
+        case BVH_LIST: return launch_persistent(k_render_stream<BVH_LIST, true>, S, R, tiles, sms, st);
+        case BVH_SAH: return launch_persistent(k_render_stream<BVH_SAH, true>, S, R, tiles, sms, st);
+        default: return launch_persistent(k_render_stream<BVH_REFERENCE, true>, S, R, tiles, sms, st);
+      }
+    }
     switch (S.bvh_kind) {
       case BVH_LIST: return launch_persistent(k_render_stream<BVH_LIST>, S, R, tiles, sms, st);
       case BVH_SAH:

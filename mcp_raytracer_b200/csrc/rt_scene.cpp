@@ -828,6 +828,7 @@ rt_status compile_scene(const rt_scene_desc* sd, const rt_render_opts* o, HostSc
   cam.mode = o->mode; cam.a_tol = (float)o->a_tolerance;
   cam.roulette = o->roulette != 0;
   cam.adaptive = (o->a_tolerance > 0 && o->samples > 1) ? 1 : 0; // camera.ts:165
+  cam.shadow_rays = o->light_sampling == RT_LIGHTS_SHADOW_RAYS ? 1 : 0;
   cam.jitter = o->samples > 1;                                    // camera.ts:184
   cam.defocus = c.aperture > 0;                                   // camera.ts:197
   return RT_OK;

@@ -90,6 +90,7 @@ struct DevCamera {
   int samples, depth, rr_depth, a_batch, mode;
   float a_tol;
   int roulette, adaptive, jitter, defocus;
+  int shadow_rays; // rt_render_opts.light_sampling == RT_LIGHTS_SHADOW_RAYS (next-event estimation)
 };
 
 struct DevScene {

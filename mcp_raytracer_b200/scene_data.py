@@ -28,6 +28,8 @@ _MODES = {"default": RT_MODE_DEFAULT, "bounces": RT_MODE_BOUNCES, "samples": RT_
 _BVH = {"auto": RT_BVH_AUTO, "reference": RT_BVH_REFERENCE, "sah": RT_BVH_SAH, "list": RT_BVH_LIST}
 _INTEGRATORS = {"auto": RT_INTEGRATOR_AUTO, "megakernel": RT_INTEGRATOR_MEGAKERNEL, "wavefront": RT_INTEGRATOR_WAVEFRONT,
                 "sorted": RT_INTEGRATOR_SORTED}
+RT_LIGHTS_MIXTURE, RT_LIGHTS_SHADOW_RAYS = 0, 1
+_LIGHTS = {"mixture": RT_LIGHTS_MIXTURE, "shadowRays": RT_LIGHTS_SHADOW_RAYS}
 
 
 class RaytracerError(Exception):
@@ -83,6 +85,7 @@ class rt_render_opts(C.Structure):
         ("device", C.c_int32),
         ("part_index", C.c_int32),
         ("part_count", C.c_int32),
+        ("light_sampling", C.c_int32),
     ]
 
 
@@ -136,6 +139,7 @@ DEFAULT_RENDER_DATA: Dict[str, Any] = {
 # knobs that exist only on this side of the boundary
 DEFAULT_NATIVE_OPTIONS: Dict[str, Any] = {
     "seed": 0, "bvh": "auto", "integrator": "auto", "device": -1, "partIndex": 0, "partCount": 1,
+    "lightSampling": "mixture",  # "shadowRays": next-event estimation (rt_b200.h RT_LIGHTS_*)
 }
 
 
@@ -166,6 +170,7 @@ def render_opts_struct(o: Dict[str, Any]) -> rt_render_opts:
         bvh=_BVH[o["bvh"]] if isinstance(o["bvh"], str) else int(o["bvh"]),
         integrator=_INTEGRATORS[o["integrator"]] if isinstance(o["integrator"], str) else int(o["integrator"]),
         device=int(o["device"]), part_index=int(o["partIndex"]), part_count=int(o["partCount"]),
+        light_sampling=_LIGHTS[o["lightSampling"]] if isinstance(o["lightSampling"], str) else int(o["lightSampling"]),
     )
 
 _OBJ_NAMES = {v: k for k, v in _OBJ_TYPES.items()}

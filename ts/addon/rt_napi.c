@@ -110,6 +110,7 @@ static void read_opts(napi_env env, napi_value o, rt_render_opts* r) { /* defaul
   r->mode = (int32_t)num_field(env, o, "mode", RT_MODE_DEFAULT); r->seed = (uint64_t)num_field(env, o, "seed", 0);
   r->bvh = RT_BVH_AUTO; r->integrator = RT_INTEGRATOR_AUTO; r->device = (int32_t)num_field(env, o, "device", -1);
   r->part_index = (int32_t)num_field(env, o, "partIndex", 0); r->part_count = (int32_t)num_field(env, o, "partCount", 1);
+  r->light_sampling = (int32_t)num_field(env, o, "lightSampling", RT_LIGHTS_MIXTURE);
 }
 /* what V8 should know about: framebuffer + fixed-point accumulator + queue per pixel, plus the scene arrays */
 static int64_t device_bytes(const rt_camera_info* ci, const rt_scene_desc* s, int n_devices) {

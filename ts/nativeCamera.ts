@@ -92,7 +92,8 @@ export function applySceneCameraOptions(sceneData: SceneData, cam?: Record<strin
   return { ...sceneData, camera, render };
 }
 
-type NativeOpts = { seed?: number, device?: number, partIndex?: number, partCount?: number, nDevices?: number };
+type NativeOpts = { seed?: number, device?: number, partIndex?: number, partCount?: number, nDevices?: number,
+                    lightSampling?: 'mixture' | 'shadowRays' };   // RT_LIGHTS_*: shadowRays = next-event estimation (not the reference's estimator)
 
 /** One GPU (`multi` false) or every visible GPU inside one call (`multi` true: rt_multi_*, the native stand-in for the
  *  worker pool of src/raytracer.ts:60-90).  Same `render` / `renderRegion` signatures as src/camera.ts:388,439. */
@@ -104,7 +105,8 @@ export class NativeCamera {
                 ...sceneData.render, ...renderOptions };   // src/camera.ts:73-83,116 ; src/scenes/scenes.ts:97-100
     this.flat = flattenScene(sceneData);
     const opts = { ...o, roulette: o.roulette ? 1 : 0, mode: MODE[o.mode as keyof typeof MODE],
-      seed: native.seed ?? 0, device: native.device ?? -1, partIndex: native.partIndex ?? 0, partCount: native.partCount ?? 1 };
+      seed: native.seed ?? 0, device: native.device ?? -1, partIndex: native.partIndex ?? 0, partCount: native.partCount ?? 1,
+      lightSampling: native.lightSampling === 'shadowRays' ? 1 : 0 };
     this.handle = multi ? addon.createMulti(this.flat, opts, native.nDevices ?? 0) : addon.createCamera(this.flat, opts);
     const info = addon.cameraInfo(this.handle);
     this.imageWidth = info.imageWidth; this.imageHeight = info.imageHeight;
