@@ -527,7 +527,7 @@ def bench_workload(args, workload, rank, world, local_rank, emit, env):
                    "bvh": {1: "reference", 2: "sah", 3: "list"}.get(cam.info.bvh_kind), "integrator": {1: "megakernel", 2: "wavefront", 3: "sorted"}.get(cam.info.integrator_kind),
                    "partition": f"8x4 pixel blocks, one per rank per run of {world} blocks, order rotated by a hash of the run (rt_block_owner)",
                    "exchange": ("none (1 GPU)" if world == 1 else "render kernels store owned pixels into rank 0's framebuffer over NVLink (CUDA IPC peer mapping); no collective"
-                                if peer_writes else "NCCL gather of each rank's owned pixels (1/N of the image)"), "rng": "Philox4x32-10 keyed (pixel,sample), counter (block,bounce)",
+                                if peer_writes else "NCCL gather of each rank's owned pixels (1/N of the image)"), "rng": "Philox4x32-7 keyed (pixel,sample), counter (block,bounce)",
                    "l2": "256 MiB memset between steps, outside the per-step CUDA-event pairs"},
         "grays_per_s": grays, "paths_per_step": paths_per_step, "rays_per_step": rays_per_step,
         "wall_s_timed_region": wall, "step_ms": step_ms,

@@ -221,7 +221,8 @@ rt_status rt_camera_render(rt_camera* cam, uint8_t* rgb8, size_t rgb8_len, float
  * [H][W][8] float) receives per pixel: sum r,g,b; the sum of squared deviations of r,g,b from the
  * pixel mean (Welford: variance = that / (samples - 1)); samples; bounces.
  * `stats_dev` (optional, device, sizeof(rt_stats)) receives the reduced statistics
- * except device_ms. */
+ * except device_ms.  Exception: RT_INTEGRATOR_WAVEFRONT drives its kernels from the host (queue counts are
+ * read back between the stages of a bounce), so with that integrator the call blocks until the render is done. */
 rt_status rt_camera_render_region_device(rt_camera* cam, const rt_region* region, uint8_t* rgb8_dev,
                                          float* linear_rgb_dev, float* moments_dev,
                                          rt_stats* stats_dev);

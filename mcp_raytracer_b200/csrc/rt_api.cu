@@ -584,7 +584,10 @@ static rt_status wf_prepare(rt_camera* c, const RenderParams& P) {
     CU(dev_alloc(&H.owned_blocks, std::max<size_t>(owned.size(), 1) * sizeof(int)));
     H.owned_capacity = (int)owned.size();
   }
-  if (!owned.empty()) CU(cudaMemcpy(H.owned_blocks, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (!owned.empty()) { // on the camera's stream (a user stream may be non-blocking: the legacy default stream does not order with it)
+    CU(cudaMemcpyAsync(H.owned_blocks, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream)); // `owned` is a pageable local
+  }
   H.n_owned = (int)owned.size();
   H.blocks_x = blocks_x;
   H.W.total_pairs = (unsigned long long)owned.size() * 32ull * (unsigned long long)std::max(0, c->hs->cam.samples);

@@ -103,7 +103,8 @@ static inline double illuminance(V3 c) { return 0.299 * c.x + 0.587 * c.y + 0.11
 // ----------------------------------------------------------------------------------------
 // Random numbers.  The reference draws from V8's Math.random (unseedable), in a fixed
 // program order per path.  The oracle keeps that draw ORDER and offers two sources:
-//   mode 0  "path-keyed Philox": Philox4x32-10, key=(pixel index, sample index),
+//   mode 0  "path-keyed Philox": Philox4x32-7 (seven rounds: the fewest that are crush-resistant, Salmon et al. SC'11;
+//           ten until round 2 — the count is the CUDA path's RT_PHILOX_ROUNDS), key=(pixel index, sample index),
 //           counter=(block, stream, seed_lo, seed_hi); stream b serves the rayColor call
 //           entered with stats.bounces == b, and the camera-ray draws of a path are the first
 //           draws of its stream 0.  A block yields FIVE 24-bit uniforms u*2^-24: the high 24
@@ -113,10 +114,14 @@ static inline double illuminance(V3 c) { return 0.299 * c.x + 0.587 * c.y + 0.11
 //   mode 1  sequential xorshift128+ (one stream per render strip, like one Math.random per
 //           worker thread), for independence checks.
 // ----------------------------------------------------------------------------------------
-static inline void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+#ifndef ORC_PHILOX_ROUNDS
+#define ORC_PHILOX_ROUNDS 7
+#endif
+static const int kPhiloxRounds = ORC_PHILOX_ROUNDS;
+static inline void philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds) {
   uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
   uint32_t k0 = key[0], k1 = key[1];
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < rounds; ++r) {
     uint64_t p0 = (uint64_t)0xD2511F53u * c0;
     uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
     uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -173,7 +178,7 @@ struct Rng {
       if (idx % 5u == 0) {
         uint32_t ctr[4] = {idx / 5u, stream, (uint32_t)seed, (uint32_t)(seed >> 32)};
         uint32_t w[4];
-        philox4x32_10(ctr, key, w);
+        philox4x32(ctr, key, w, kPhiloxRounds);
         for (int k = 0; k < 4; ++k) buf[k] = w[k] >> 8;
         buf[4] = ((w[0] & 0xffu) << 16) | ((w[1] & 0xffu) << 8) | (w[2] & 0xffu);
       }
@@ -1220,7 +1225,8 @@ int orc_get_ray(void* cam, int i, int j, uint32_t sample, uint64_t seed, float* 
 }
 
 // ---- unit hooks for the reference's known-answer vectors --------------------------------
-void orc_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
+void orc_philox4x32(const uint32_t* ctr, const uint32_t* key, int rounds, uint32_t* out) { philox4x32(ctr, key, out, rounds); }
+int orc_philox_rounds(void) { return kPhiloxRounds; } // rounds of the path-keyed streams (the CUDA path's RT_PHILOX_ROUNDS)
 
 // uniforms of the path-keyed stream (so tests can predict draws)
 void orc_stream_uniforms(uint32_t pixel, uint32_t sample, uint32_t stream, uint64_t seed, int n, double* out) {

@@ -67,7 +67,8 @@ def lib() -> C.CDLL:
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_ray_color.argtypes = [C.c_void_p, fp, fp, C.c_uint32, C.c_uint32, C.c_uint64, fp, C.POINTER(C.c_int)]
         L.orc_get_ray.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, fp, fp]
-        L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.orc_philox4x32.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.POINTER(C.c_uint32)]
+        L.orc_philox_rounds.restype = C.c_int
         L.orc_stream_uniforms.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int, dp]
         L.orc_sphere_hit.argtypes = [dp, C.c_double, dp, dp, C.c_double, C.c_double, dp]
         L.orc_sphere_pdf_value.argtypes = [dp, C.c_double, dp, dp]

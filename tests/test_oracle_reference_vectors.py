@@ -34,16 +34,22 @@ def unit(v):
 
 
 # ---------------------------------------------------------------- Philox (Random123 KAT)
-def test_philox4x32_10_known_answers():
-    def ph(ctr, key):
+def test_philox4x32_known_answers():
+    """Random123's kat_vectors for philox4x32 at 10 rounds (its default) and at 7 (the fewest that are crush-resistant,
+    Salmon et al., SC'11 table 2)."""
+    def ph(ctr, key, rounds):
         out = (C.c_uint32 * 4)()
-        lib().orc_philox4x32_10((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out)
+        lib().orc_philox4x32((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), rounds, out)
         return list(out)
 
-    assert ph([0] * 4, [0] * 2) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
-    assert ph([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
-    assert ph([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0]) == [
-        0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    pi = ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0])
+    assert ph([0] * 4, [0] * 2, 10) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert ph([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, 10) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    assert ph(*pi, 10) == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+    assert ph([0] * 4, [0] * 2, 7) == [0x5F6FB709, 0x0D893F64, 0x4F121F81, 0x4F730A48]
+    assert ph([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, 7) == [0x5207DDC2, 0x45165E59, 0x4D8EE751, 0x8C52F662]
+    assert ph(*pi, 7) == [0x4DFCCABA, 0x190A87F0, 0xC47362BA, 0xB6B5242A]
+    assert lib().orc_philox_rounds() in (7, 10)
 
 
 # ---------------------------------------------------------------- tests/entities/sphere.test.ts
