@@ -25,6 +25,7 @@ namespace rt {
 cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms, cudaStream_t st);
 void render_tile_grid(const RenderParams& R, int* tiles_x, int* tiles_y);
 bool render_needs_full(const DevScene& S, const RenderParams& R);
+int render_adaptive_blocks(const DevScene& S, const RenderParams& R, int sms, int* warps);
 cudaError_t launch_trace_primary(const DevScene& S, const RenderParams& R, int* obj_id, float* t, float* normal,
                                  uint8_t* front, cudaStream_t st);
 cudaError_t launch_fp32_peak(float* out, int blocks, int iters, cudaStream_t st);
@@ -177,6 +178,8 @@ struct rt_camera {
   size_t queue_ints = 0;
   unsigned long long* d_scratch = nullptr; // fixed-point radiance sums [H][W][4]
   PixState* d_pixstate = nullptr;          // progressive renders of the pixel-stream kernels: PixelStats between passes
+  AdRecord* d_adrec = nullptr;             // k_render_adaptive: per-warp sample records of the batch in flight
+  size_t adrec_elems = 0;
   size_t scratch_elems = 0;
   int sms = 0;
   int chunks = 1;
@@ -216,7 +219,7 @@ static void free_camera(rt_camera* c) {
   cudaStreamSynchronize(c->stream); // the blocks go back to the cache: nothing of this camera may still be in flight
   for (void* p : c->allocs) dev_free(p);
   dev_free(c->d_rgb8); dev_free(c->d_linear); dev_free(c->d_moments); dev_free(c->d_ids);
-  dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch); dev_free(c->d_pixstate);
+  dev_free(c->d_t); dev_free(c->d_normal); dev_free(c->d_front); dev_free(c->d_stats); dev_free(c->d_queue); dev_free(c->d_scratch); dev_free(c->d_pixstate); dev_free(c->d_adrec);
   wf_release(c);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -638,6 +641,26 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
         P.div_samples = pass->s1;
         P.keep_accum = 1;
         P.chunks = std::max(1, std::min(P.chunks, P.s_cnt));
+      }
+    }
+    {
+      // plain adaptive renders: batch-parallel kernel (k_render_adaptive); PixelStats between batches reuse the pass buffer
+      int warps = 0;
+      const int gb = pass ? 0 : render_adaptive_blocks(c->ds, P, c->sms, &warps);
+      if (gb > 0) {
+        if (!c->d_pixstate) CU(dev_alloc(&c->d_pixstate, (size_t)c->hs->image_width * c->hs->image_height * sizeof(PixState)));
+        const size_t need_r = (size_t)warps * gb * 32 * (size_t)c->hs->cam.a_batch;
+        if (need_r > c->adrec_elems) {
+          CU(cudaStreamSynchronize(c->stream));
+          dev_free(c->d_adrec);
+          c->d_adrec = nullptr;
+          c->adrec_elems = 0;
+          CU(dev_alloc(&c->d_adrec, need_r * sizeof(AdRecord)));
+          c->adrec_elems = need_r;
+        }
+        P.adstate = c->d_pixstate;
+        P.adrec = c->d_adrec;
+        P.ad_blocks = gb;
       }
     }
     const size_t need_q = 1 + std::max((size_t)P.tiles_x * P.tiles_y * 8, (size_t)P.n_runs); // queue head + one completion counter per 8x4 block / run

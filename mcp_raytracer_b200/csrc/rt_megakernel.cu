@@ -27,6 +27,8 @@
 //
 // All path state lives in registers; HBM sees the scene reads (L1/L2 resident), 24 B of atomics per
 // (pixel, chunk) when chunks > 1, and 3 bytes per pixel of output.
+#include <algorithm>
+
 #include "rt_device.cuh"
 
 namespace rt {
@@ -1511,6 +1513,211 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
 }
 
 // =========================================================================================
+// k_render_adaptive — adaptive sampling (the reference's default) at the lane occupancy of the fixed-spp kernels.
+//
+// k_render_stream gives a pixel to ONE lane until it converges: camera.ts:348-368 decides after every aBatch samples whether
+// the pixel goes on, so its samples cannot be dealt out freely.  But the decision only needs the batch to be COMPLETE, not to
+// have run on one lane.  Here the unit of work is one batch of a GROUP of pixels (1-4 8x4 blocks): the (pixel, sample)
+// pairs of the group's still active pixels x aBatch samples form a pool that the 32 lanes drain with the pair queue of
+// k_render_pool<.., true> (a lane whose path ends takes the next pair: no lane waits for a neighbour's long pixel); every
+// finished sample is written as a 16-byte record (radiance, bounces) into the warp's slice of a scratch array; when the pool
+// is dry each pixel's records are added to its PixelStats IN SAMPLE ORDER by one lane — the very sequence of FP32 / FP64
+// additions k_render_stream performs — followed by the convergence test.  Same streams, same sums, same decisions: the image
+// and the statistics are those of k_render_stream bit for bit (tests/test_gpu_parity.py compares the two kernels).
+// A group's batches must run one after the other; the groups are independent.  The queue deals out (batch r, group g)
+// batch-major, a warp that pops (r, g) waits for tile_done[g] == r (by then (r - 1, g) was popped a whole round of groups
+// earlier: the wait is almost never taken; every CTA of the persistent grid is resident, so the owner of (r - 1, g) runs),
+// and groups whose pixels are all final are skipped with one load.  No kernel-wide barrier between batches, and the tail of
+// the render is one batch of one group instead of one whole pixel (17 ms at 1024 spp).
+// =========================================================================================
+#ifndef RT_ADAPT_BLOCKS
+#define RT_ADAPT_BLOCKS 2
+#endif
+// PixelStats between two batches.  Written by one SM, read by another a batch later: L2 accesses (ld.cg / st.cg), the L1 of the
+// reading SM may still hold the line from an earlier batch.
+RT_DEV void adstate_load(const PixState* ps, size_t pi, float& cx, float& cy, float& cz, double& s1, double& s2, int& samples, unsigned& bounces) {
+  const long long* p = reinterpret_cast<const long long*>(ps + pi); // 40 bytes, 8-byte aligned
+  const long long w0 = __ldcg(p), w1 = __ldcg(p + 1), w2 = __ldcg(p + 2), w3 = __ldcg(p + 3), w4 = __ldcg(p + 4);
+  cx = __int_as_float((int)(w0 & 0xffffffffLL)); cy = __int_as_float((int)(w0 >> 32));
+  cz = __int_as_float((int)(w1 & 0xffffffffLL)); samples = (int)(w1 >> 32);
+  s1 = __longlong_as_double(w2); s2 = __longlong_as_double(w3);
+  bounces = (unsigned)(w4 & 0xffffffffLL);
+}
+RT_DEV void adstate_store(PixState* ps, size_t pi, float cx, float cy, float cz, double s1, double s2, int samples, unsigned bounces, int done) {
+  long long* p = reinterpret_cast<long long*>(ps + pi);
+  auto pack = [](unsigned lo, unsigned hi) { return (long long)(((unsigned long long)hi << 32) | lo); };
+  __stcg(p, pack((unsigned)__float_as_int(cx), (unsigned)__float_as_int(cy)));
+  __stcg(p + 1, pack((unsigned)__float_as_int(cz), (unsigned)samples));
+  __stcg(p + 2, __double_as_longlong(s1));
+  __stcg(p + 3, __double_as_longlong(s2));
+  __stcg(p + 4, pack(bounces, (unsigned)done));
+}
+constexpr int kAdMaxBlocks = 4;       // 8x4 blocks per group
+constexpr int kAdMaxRecords = 1280;   // records per warp slice: ad_blocks * 32 * aBatch <= this
+
+template <int KIND>
+__global__ void __launch_bounds__(256, RT_ADAPT_BLOCKS) k_render_adaptive(const DevScene S, const RenderParams R) {
+  __shared__ ListSmemData sm_data;
+  __shared__ unsigned char s_slot[8][kAdMaxBlocks * 32]; // per warp: the group's active pixels (index inside the group), packed
+  __shared__ int s_blk[8][2 * kAdMaxBlocks];             // per warp: pixel origin of each block of the group
+  const ListSmem sm = stage_list<KIND>(S, sm_data);
+  const ListSmem& L = sm;
+  const DevCamera& cam = S.cam;
+  const MixW mw = make_mixw(S);
+  const unsigned lane = threadIdx.x & 31u, full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+  const int warp = (int)(threadIdx.x >> 5);
+  unsigned char* slot_px = s_slot[warp];
+  int* blk = s_blk[warp];
+  const int B = cam.a_batch, GB = R.ad_blocks;
+  AdRecord* rec = R.adrec + (size_t)(blockIdx.x * 8 + warp) * (size_t)(GB * 32 * B);
+  const int blocks_x = R.tiles_x * 2, blocks_per_row = (cam.width + 7) >> 3;
+  const int n_blocks = R.part_count > 1 ? R.n_runs : blocks_x * R.tiles_y * 4;
+  const int n_groups = (n_blocks + GB - 1) / GB;
+  const int n_rounds = (cam.samples + B - 1) / B;
+  const int n_items = n_groups * n_rounds;
+
+  unsigned int t_pixels = 0, t_samples = 0, t_bounces = 0;
+  WorkCount wc;
+  int t_smin = 0x7fffffff, t_smax = 0, t_bmin = 0x7fffffff, t_bmax = 0;
+
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(R.queue, 1);
+    item = __shfl_sync(full, item, 0);
+    if (item >= n_items) break;
+    const int round = item / n_groups, g = item - round * n_groups;
+    // ---- the group's earlier batches must be complete ----
+    volatile int* done_rounds = R.tile_done + g;
+    int have = 0;
+    if (lane == 0) {
+      while ((have = *done_rounds) < round) __nanosleep(200);
+    }
+    have = __shfl_sync(full, have, 0);
+    if (have > round) continue; // INT_MAX: every pixel of the group is final
+    __threadfence();            // the PixelStats written by the warp that ran the previous batch
+    // ---- the group's blocks and its active pixels ----
+    if ((int)lane < GB) {
+      const int b = g * GB + (int)lane;
+      int bx = -(1 << 20), by = -(1 << 20);
+      if (b < n_blocks) {
+        if (R.part_count > 1) {
+          const unsigned i = owned_block_of_run((unsigned)(R.run0 + b), R.part_index, R.part_count);
+          bx = (int)(i % (unsigned)blocks_per_row) * 8;
+          by = (int)(i / (unsigned)blocks_per_row) * 4;
+        } else {
+          bx = (R.x0 / kTile) * kTile + (b % blocks_x) * 8;
+          by = (R.y0 / kTile) * kTile + (b / blocks_x) * 4;
+        }
+      }
+      blk[2 * lane] = bx;
+      blk[2 * lane + 1] = by;
+    }
+    __syncwarp();
+    const int s_done = round * B, Bc = min(B, cam.samples - s_done); // every active pixel of the group has s_done samples
+    int n_active = 0;
+    for (int k = 0; k < GB; ++k) {
+      const int x = blk[2 * k] + (int)(lane & 7u), y = blk[2 * k + 1] + (int)(lane >> 3);
+      bool act = x >= R.x0 && x < R.x1 && y >= R.y0 && y < R.y1;
+      if (act && round > 0) act = __ldcg(&R.adstate[(size_t)y * cam.width + x].done) == 0;
+      const unsigned m = __ballot_sync(full, act);
+      if (act) slot_px[n_active + __popc(m & lt_mask)] = (unsigned char)(k * 32 + (int)lane);
+      n_active += __popc(m);
+    }
+    __syncwarp();
+    if (n_active == 0) { // nothing of this group lies in the region
+      if (lane == 0) *done_rounds = 0x7fffffff;
+      continue;
+    }
+    // ---- the pool: n_active pixels x Bc samples, sample-major (neighbouring lanes run the same sample of different pixels) ----
+    const int pool = n_active * Bc;
+    {
+      PathState ps{Ray{mk3(0, 0, 0), mk3(0, 0, 1)}, mk3(1, 1, 1), mk3(0, 0, 0), 0};
+      Rng gen;
+      int slot = 0, s_in = 0, pi_x = 0, pi_y = 0, next = 0;
+      bool have_path = false, retired = false;
+      for (;;) {
+        const bool want = !have_path && !retired;
+        bool fresh = false;
+        const unsigned m = __ballot_sync(full, want);
+        if (want) {
+          const int idx = next + __popc(m & lt_mask);
+          if (idx >= pool) retired = true;
+          else {
+            s_in = idx / n_active;
+            slot = idx - s_in * n_active;
+            const int q = slot_px[slot];
+            pi_x = blk[2 * (q >> 5)] + (q & 7);
+            pi_y = blk[2 * (q >> 5) + 1] + ((q >> 3) & 3);
+            fresh = true;
+            have_path = true;
+          }
+        }
+        next += __popc(m);
+        if (__all_sync(full, retired)) break;
+        bool ended = false;
+        if (have_path) {
+          const uint32_t pixel = (uint32_t)pi_y * (uint32_t)cam.width + (uint32_t)pi_x;
+          if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
+          gen.begin(pixel, (uint32_t)(s_done + s_in), (uint32_t)ps.bounces, S.seed_lo, S.seed_hi);
+          if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, gen, true);
+          ended = path_step<KIND, false>(S, L, sm, mw, ps, gen, wc);
+        }
+        __syncwarp(); // one copy of the end-of-sample code (see k_render_pool)
+        if (ended) {
+          AdRecord r{ps.radiance.x, ps.radiance.y, ps.radiance.z, ps.bounces};
+          __stcg(reinterpret_cast<float4*>(rec + slot * B + s_in), *reinterpret_cast<const float4*>(&r));
+          t_bmin = min(t_bmin, ps.bounces);
+          t_bmax = max(t_bmax, ps.bounces);
+          have_path = false;
+        }
+      }
+    }
+    __syncwarp(); // the records of every lane are visible to the lane that folds the pixel
+    // ---- pixel.add(...) of the batch in sample order + the loop condition of camera.ts:406, one lane per pixel ----
+    int remaining = 0;
+    for (int slot = (int)lane; slot < n_active; slot += 32) {
+      const int q = slot_px[slot];
+      const int x = blk[2 * (q >> 5)] + (q & 7), y = blk[2 * (q >> 5) + 1] + ((q >> 3) & 3);
+      const size_t pi = (size_t)y * cam.width + x;
+      float cx = 0.f, cy = 0.f, cz = 0.f;
+      double s1 = 0.0, s2 = 0.0;
+      int samples = 0;
+      unsigned bounces = 0;
+      if (round > 0) adstate_load(R.adstate, pi, cx, cy, cz, s1, s2, samples, bounces);
+      float b_ill = 0.f, b_ill2 = 0.f;
+      for (int k = 0; k < Bc; ++k) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(rec + slot * B + k));
+        cx += v.x; cy += v.y; cz += v.z;
+        bounces += (unsigned)__float_as_int(v.w);
+        const float il = fmaf(0.299f, v.x, fmaf(0.587f, v.y, 0.114f * v.z)); // illuminance (vec3.ts:239-242)
+        b_ill += il;
+        b_ill2 = fmaf(il, il, b_ill2);
+        t_bounces += (unsigned)__float_as_int(v.w);
+      }
+      samples += Bc;
+      t_samples += (unsigned)Bc;
+      s1 += (double)b_ill;
+      s2 += (double)b_ill2;
+      bool final_ = samples >= cam.samples;
+      if (!final_ && Bc == B && samples >= 2) final_ = pixel_converged(s1, s2, samples, cam.a_tol); // camera.ts:348-368
+      if (final_) {
+        stream_write_pixel(R.rgb8, R.linear, nullptr, cam.width, 0, cam.depth, cam.samples, x, y, samples, bounces, cx, cy, cz, 0.f, 0.f, 0.f);
+        ++t_pixels;
+        t_smin = min(t_smin, samples);
+        t_smax = max(t_smax, samples);
+      } else ++remaining;
+      adstate_store(R.adstate, pi, cx, cy, cz, s1, s2, samples, bounces, final_ ? 1 : 0);
+    }
+    const unsigned any_left = __ballot_sync(full, remaining > 0);
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) *done_rounds = any_left ? round + 1 : 0x7fffffff;
+  }
+  flush_stats_range(R, t_pixels, t_smin, t_smax, t_samples, t_bounces, wc.rays, t_bmin, t_bmax);
+  flush_work(R, wc);
+}
+
+// =========================================================================================
 // primary visibility (parity hook): pixel-centre rays, no jitter, no defocus
 // =========================================================================================
 template <int KIND>
@@ -1566,6 +1773,34 @@ void render_tile_grid(const RenderParams& R, int* tiles_x, int* tiles_y) {
   int tx1 = (R.x1 - 1) / kTile, ty1 = (R.y1 - 1) / kTile;
   *tiles_x = tx1 - tx0 + 1;
   *tiles_y = ty1 - ty0 + 1;
+}
+
+// k_render_adaptive: plain adaptive renders (default mode, no moments, one shot) of every scene the whole-query kernels serve.
+// Returns the group size in 8x4 blocks (0 = the pixel-stream kernels render this), and the number of warps whose record
+// slices `adrec` must hold.
+constexpr int kTravNodesAdaptive = 16384; // deep trees keep k_render_stream_trav (resumable traversal)
+int render_adaptive_blocks(const DevScene& S, const RenderParams& R, int sms, int* warps) {
+  static const bool off = getenv("RT_B200_NO_ADAPTIVE_POOL") != nullptr; // development switch
+  if (off || !S.cam.adaptive || S.cam.mode != 0 || R.moments || S.cam.shadow_rays || R.pixstate || R.pass_cap > 0) return 0;
+  if (S.cam.a_batch < 1 || S.cam.a_batch * 32 > kAdMaxRecords) return 0;
+  if (S.bvh_kind == BVH_SAH && S.n_nodes >= kTravNodesAdaptive) return 0;
+  int per_sm = 0;
+  cudaError_t e;
+  switch (S.bvh_kind) {
+    case BVH_LIST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_LIST>, 256, 0); break;
+    case BVH_SAH: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_SAH>, 256, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_REFERENCE>, 256, 0); break;
+  }
+  if (e != cudaSuccess || per_sm < 1) return 0;
+  const long long n_warps = (long long)sms * per_sm * 8;
+  const long long n_blocks = R.part_count > 1 ? R.n_runs : (long long)R.tiles_x * R.tiles_y * 8;
+  // groups as large as the record slice allows (longer pools, shorter tails) while every warp still finds two groups
+  long long gb = std::min<long long>(kAdMaxBlocks, kAdMaxRecords / (32 * S.cam.a_batch));
+  while (gb > 1 && n_blocks / gb < 2 * n_warps) --gb;
+  const long long n_groups = (n_blocks + gb - 1) / gb, n_rounds = (S.cam.samples + S.cam.a_batch - 1) / S.cam.a_batch;
+  if (n_groups * n_rounds >= (1LL << 30)) return 0;
+  if (warps) *warps = (int)n_warps;
+  return (int)gb;
 }
 
 bool render_needs_full(const DevScene& S, const RenderParams& R) {
@@ -1625,6 +1860,13 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
         case BVH_LIST: return launch_persistent(k_render_stream<BVH_LIST, true>, S, R, tiles, sms, st);
         case BVH_SAH: return launch_persistent(k_render_stream<BVH_SAH, true>, S, R, tiles, sms, st);
         default: return launch_persistent(k_render_stream<BVH_REFERENCE, true>, S, R, tiles, sms, st);
+      }
+    }
+    if (R.ad_blocks > 0) { // chosen by render_adaptive_blocks (rt_api.cu sizes adstate / adrec from it)
+      switch (S.bvh_kind) {
+        case BVH_LIST: return launch_persistent(k_render_adaptive<BVH_LIST>, S, R, 1LL << 40, sms, st);
+        case BVH_SAH: return launch_persistent(k_render_adaptive<BVH_SAH>, S, R, 1LL << 40, sms, st);
+        default: return launch_persistent(k_render_adaptive<BVH_REFERENCE>, S, R, 1LL << 40, sms, st);
       }
     }
     switch (S.bvh_kind) {

@@ -167,6 +167,17 @@ struct RenderParams {
   // its PixelStats live in pixstate between passes (null: one-shot render)
   struct PixState* pixstate;
   int pass_cap;
+  // ---- batch-parallel adaptive sampling (k_render_adaptive) ----
+  // PixelStats of every pixel between two batches live in `adstate` [H][W]; a warp item = one batch (aBatch samples) of the still
+  // active pixels of a group of ad_blocks 8x4 blocks, its per-sample records in this warp's slice of `adrec`; tile_done[group] =
+  // batches the group has completed (INT_MAX: every pixel final)
+  struct PixState* adstate;
+  struct AdRecord* adrec; // [resident warps][ad_blocks * 32 * aBatch]
+  int ad_blocks;
+};
+struct alignas(16) AdRecord { // one finished sample: pixel.add(rayColor, bounces) waiting for its turn in the pixel's sum
+  float r, g, b;
+  int bounces;
 };
 // PixelStats of one pixel between two passes of a progressive render (renderStats.ts:67-88)
 struct alignas(8) PixState {

@@ -1,7 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python scripts/gpu_full_parity.py r02b > gpurun_out/r02b_full_parity.log 2>&1; tail -3 gpurun_out/r02b_full_parity.log | cut -c1-300; python - <<'PY'
-import json
-for r in json.load(open("gpurun_out/r02b_full_parity.json")):
-    print(r.get("case"), r.get("bars_met"), r.get("frac_within_3sigma"), r.get("rel_rmse_raw"), r.get("rel_rmse_noise_floor"), r.get("z2_mean"), r.get("ids_differ"), r.get("gpu_nonfinite_pixels"), r.get("oracle_nonfinite_pixels"))
-PY
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "adaptive" > gpurun_out/r02c_pytest_adaptive.log 2>&1; tail -5 gpurun_out/r02c_pytest_adaptive.log
+(echo "== k_render_adaptive"; timeout 200 python scripts/gpu_adaptive.py 0 0 C2 C3 C5 C1; echo "== pixel stream (RT_B200_NO_ADAPTIVE_POOL=1)"; RT_B200_NO_ADAPTIVE_POOL=1 timeout 200 python scripts/gpu_adaptive.py 0 0 C2 C3 C5 C1) > gpurun_out/r02c_adaptive_ab.log 2>&1
+cat gpurun_out/r02c_adaptive_ab.log

@@ -385,6 +385,34 @@ def test_adaptive_pixel_stream_regions_and_partitions(gpu, name, bvh):
     assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], whole["rgb8"][inside])
 
 
+@pytest.mark.parametrize("name,opts", [
+    ("C2-cornell", {"width": 160, "samples": 200}),                                   # LIST, groups of 4 blocks
+    ("C2-cornell", {"width": 96, "samples": 50, "aBatch": 7}),                        # last batch shorter than aBatch
+    ("C1-spheres", {"width": 200, "samples": 100}),                                   # SAH whole-query walk, most pixels stop at 10
+    ("C3-weekend", {"width": 160, "samples": 60, "aTolerance": 0.02}),
+    ("C5-layered", {"width": 96, "samples": 64, "aBatch": 40}),                       # one block per group (record slice)
+    ("default", {"width": 120, "samples": 40, "bvh": "reference"}),
+    ("C2-cornell", {"width": 64, "samples": 90, "aBatch": 41}),                       # aBatch too large for a record slice: the stream kernel renders it
+])
+def test_batch_parallel_adaptive_kernel_equals_the_pixel_stream(gpu, name, opts):
+    """k_render_adaptive (plain adaptive renders) deals a pixel's batch out over the lanes of a warp and adds the samples back
+    in order: image, sample counts and statistics are those of k_render_stream (which renders when moments are asked for)."""
+    sd = SCENES[name]()
+    opts = {"aTolerance": 0.05, "aBatch": 10, "seed": 31, **opts}
+    a = gpu_render(sd, opts)
+    b = gpu_render(sd, opts, want_moments=True)
+    assert np.array_equal(a["linear"], b["linear"]) and np.array_equal(a["rgb8"], b["rgb8"])
+    sa, sb = a["stats"], b["stats"]
+    assert (sa.pixels, sa.samples, sa.bounces, sa.rays) == (sb.pixels, sb.samples, sb.bounces, sb.rays)
+    assert sa.samples["min"] < sa.samples["max"] or name == "C5-layered"     # the exit rule is really exercised
+    # a ragged region: the same pixels
+    H, W = a["rgb8"].shape[:2]
+    reg = {"x": 5, "y": 3, "width": W - 11, "height": H - 9}
+    c = gpu_render(sd, opts, region=reg)
+    ys, xs = slice(reg["y"], reg["y"] + reg["height"]), slice(reg["x"], reg["x"] + reg["width"])
+    assert np.array_equal(c["linear"][ys, xs], a["linear"][ys, xs])
+
+
 def test_zero_samples_gives_black_image(gpu):  # while (pixel.samples < 0) never runs: colour/0 -> NaN -> 0 (camera.ts:406, :455-472)
     g = gpu_render(SCENES["C2-cornell"](), {"width": 40, "samples": 0})
     assert g["stats"].pixels == 1600 and g["stats"].samples["total"] == 0
