@@ -360,7 +360,7 @@ rt_status rt_scene_validate(const rt_scene_desc* scene, const rt_render_opts* op
         const int ref = W[idx].ref[k];
         if (ref == kEmptyRef) continue;
         B cb;
-        for (int a = 0; a < 3; ++a) { cb.mn[a] = W[idx].box[k][a]; cb.mx[a] = W[idx].box[k][3 + a]; }
+        for (int a = 0; a < 3; ++a) { cb.mn[a] = W[idx].box[k][a] - W[idx].box[k][3 + a]; cb.mx[a] = W[idx].box[k][a] + W[idx].box[k][3 + a]; } // (centre, half-extent)
         if (!inside(cb, pbox)) ++errors;
         if (ref < 0) check_leaf(ref, cb);
         else todo.push_back({ref, cb});

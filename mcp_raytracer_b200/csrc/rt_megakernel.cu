@@ -1530,9 +1530,23 @@ __global__ void __launch_bounds__(256, RT_MIN_BLOCKS) k_render_stream_trav(const
 // and groups whose pixels are all final are skipped with one load.  No kernel-wide barrier between batches, and the tail of
 // the render is one batch of one group instead of one whole pixel (17 ms at 1024 spp).
 // =========================================================================================
+// CTA shape per scene kind (Cornell 1024 spp / weekend-final 512 spp with the reference's defaults, ms): the list walk runs best
+// at 20 warps of 96 registers (128 x 5: 114.6; 256 x 2: 120.3; 128 x 6 at 80 registers: 124.0; 192 x 3: 116.8), the tree walks
+// at 16 warps of 128 (256 x 2: 209; 128 x 5: 256; 128 x 6: 303) — r02c_adaptive_variants2.log
+#ifndef RT_ADAPT_LIST_THREADS
+#define RT_ADAPT_LIST_THREADS 128
+#endif
+#ifndef RT_ADAPT_LIST_BLOCKS
+#define RT_ADAPT_LIST_BLOCKS 5
+#endif
 #ifndef RT_ADAPT_BLOCKS
 #define RT_ADAPT_BLOCKS 2
 #endif
+#ifndef RT_ADAPT_THREADS
+#define RT_ADAPT_THREADS 256
+#endif
+__host__ __device__ constexpr int ad_threads(int kind) { return kind == BVH_LIST ? RT_ADAPT_LIST_THREADS : RT_ADAPT_THREADS; }
+__host__ __device__ constexpr int ad_blocks(int kind) { return kind == BVH_LIST ? RT_ADAPT_LIST_BLOCKS : RT_ADAPT_BLOCKS; }
 // PixelStats between two batches.  Written by one SM, read by another a batch later: L2 accesses (ld.cg / st.cg), the L1 of the
 // reading SM may still hold the line from an earlier batch.
 RT_DEV void adstate_load(const PixState* ps, size_t pi, float& cx, float& cy, float& cz, double& s1, double& s2, int& samples, unsigned& bounces) {
@@ -1552,14 +1566,18 @@ RT_DEV void adstate_store(PixState* ps, size_t pi, float cx, float cy, float cz,
   __stcg(p + 3, __double_as_longlong(s2));
   __stcg(p + 4, pack(bounces, (unsigned)done));
 }
-constexpr int kAdMaxBlocks = 4;       // 8x4 blocks per group
-constexpr int kAdMaxRecords = 1280;   // records per warp slice: ad_blocks * 32 * aBatch <= this
+#ifndef RT_ADAPT_MAXBLOCKS
+#define RT_ADAPT_MAXBLOCKS 4
+#endif
+constexpr int kAdMaxBlocks = RT_ADAPT_MAXBLOCKS;        // 8x4 blocks per group (the slot index k * 32 + lane is a byte: <= 8)
+constexpr int kAdMaxRecords = 320 * kAdMaxBlocks;       // records per warp slice: ad_blocks * 32 * aBatch <= this
 
 template <int KIND>
-__global__ void __launch_bounds__(256, RT_ADAPT_BLOCKS) k_render_adaptive(const DevScene S, const RenderParams R) {
+__global__ void __launch_bounds__(ad_threads(KIND), ad_blocks(KIND)) k_render_adaptive(const DevScene S, const RenderParams R) {
+  constexpr int kAdWarps = ad_threads(KIND) / 32;
   __shared__ ListSmemData sm_data;
-  __shared__ unsigned char s_slot[8][kAdMaxBlocks * 32]; // per warp: the group's active pixels (index inside the group), packed
-  __shared__ int s_blk[8][2 * kAdMaxBlocks];             // per warp: pixel origin of each block of the group
+  __shared__ unsigned char s_slot[kAdWarps][kAdMaxBlocks * 32]; // per warp: the group's active pixels (index inside the group), packed
+  __shared__ int s_blk[kAdWarps][2 * kAdMaxBlocks];             // per warp: pixel origin of each block of the group
   const ListSmem sm = stage_list<KIND>(S, sm_data);
   const ListSmem& L = sm;
   const DevCamera& cam = S.cam;
@@ -1569,7 +1587,7 @@ __global__ void __launch_bounds__(256, RT_ADAPT_BLOCKS) k_render_adaptive(const 
   unsigned char* slot_px = s_slot[warp];
   int* blk = s_blk[warp];
   const int B = cam.a_batch, GB = R.ad_blocks;
-  AdRecord* rec = R.adrec + (size_t)(blockIdx.x * 8 + warp) * (size_t)(GB * 32 * B);
+  AdRecord* rec = R.adrec + (size_t)(blockIdx.x * kAdWarps + warp) * (size_t)(GB * 32 * B);
   const int blocks_x = R.tiles_x * 2, blocks_per_row = (cam.width + 7) >> 3;
   const int n_blocks = R.part_count > 1 ? R.n_runs : blocks_x * R.tiles_y * 4;
   const int n_groups = (n_blocks + GB - 1) / GB;
@@ -1787,12 +1805,12 @@ int render_adaptive_blocks(const DevScene& S, const RenderParams& R, int sms, in
   int per_sm = 0;
   cudaError_t e;
   switch (S.bvh_kind) {
-    case BVH_LIST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_LIST>, 256, 0); break;
-    case BVH_SAH: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_SAH>, 256, 0); break;
-    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_REFERENCE>, 256, 0); break;
+    case BVH_LIST: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_LIST>, ad_threads(BVH_LIST), 0); break;
+    case BVH_SAH: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_SAH>, ad_threads(BVH_SAH), 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_render_adaptive<BVH_REFERENCE>, ad_threads(BVH_REFERENCE), 0); break;
   }
   if (e != cudaSuccess || per_sm < 1) return 0;
-  const long long n_warps = (long long)sms * per_sm * 8;
+  const long long n_warps = (long long)sms * per_sm * (ad_threads(S.bvh_kind) / 32);
   const long long n_blocks = R.part_count > 1 ? R.n_runs : (long long)R.tiles_x * R.tiles_y * 8;
   // groups as large as the record slice allows (longer pools, shorter tails) while every warp still finds two groups
   long long gb = std::min<long long>(kAdMaxBlocks, kAdMaxRecords / (32 * S.cam.a_batch));
@@ -1864,9 +1882,9 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
     }
     if (R.ad_blocks > 0) { // chosen by render_adaptive_blocks (rt_api.cu sizes adstate / adrec from it)
       switch (S.bvh_kind) {
-        case BVH_LIST: return launch_persistent(k_render_adaptive<BVH_LIST>, S, R, 1LL << 40, sms, st);
-        case BVH_SAH: return launch_persistent(k_render_adaptive<BVH_SAH>, S, R, 1LL << 40, sms, st);
-        default: return launch_persistent(k_render_adaptive<BVH_REFERENCE>, S, R, 1LL << 40, sms, st);
+        case BVH_LIST: return launch_persistent(k_render_adaptive<BVH_LIST>, S, R, 1LL << 40, sms, st, ad_threads(BVH_LIST));
+        case BVH_SAH: return launch_persistent(k_render_adaptive<BVH_SAH>, S, R, 1LL << 40, sms, st, ad_threads(BVH_SAH));
+        default: return launch_persistent(k_render_adaptive<BVH_REFERENCE>, S, R, 1LL << 40, sms, st, ad_threads(BVH_REFERENCE));
       }
     }
     switch (S.bvh_kind) {

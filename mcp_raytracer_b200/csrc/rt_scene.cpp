@@ -541,9 +541,22 @@ struct Flattener {
     S.nodes.emplace_back();
     WideNode w;
     for (int k = 0; k < 4; ++k) {
-      const Box b = k < nc ? pool[c[k]].box : empty_box();
-      std::memcpy(w.box[k], b.mn, 12);
-      std::memcpy(w.box[k] + 3, b.mx, 12);
+      for (int a = 0; a < 3; ++a) { // (centre, half-extent), half-extent rounded up: the stored box contains the builder's
+        float ctr = 0.f, half = -INFINITY; // unused child: never hit
+        if (k < nc) {
+          const double mn = pool[c[k]].box.mn[a], mx = pool[c[k]].box.mx[a];
+          if (!std::isfinite(mn) || !std::isfinite(mx)) half = INFINITY; // unbounded on this axis
+          else {
+            ctr = (float)(0.5 * (mn + mx));
+            // an inverted box (negative-radius sphere) keeps its extent: the min / max slab test never cared about the order
+            const double hd = std::max(std::fabs(mx - (double)ctr), std::fabs((double)ctr - mn));
+            half = (float)hd;
+            if ((double)half < hd) half = std::nextafter(half, INFINITY);
+          }
+        }
+        w.box[k][a] = ctr;
+        w.box[k][3 + a] = half;
+      }
       w.ref[k] = kEmptyRef;
       w.pad[k] = 0;
     }

@@ -56,7 +56,9 @@ struct alignas(16) Node { // 64 B
 };
 
 // SAH trees: four children per node (the binary tree collapsed, rt_scene.cpp), 128 B = two Node slots.
-// box[k] = (min.xyz, max.xyz) of child k, ref[k] as above; unused children: inverted box + kEmptyRef.
+// box[k] = (centre.xyz, half-extent.xyz) of child k — the slab test is then three FFMA per axis and no per-axis min / max
+// (trav_inner, rt_device.cuh); the half-extents are rounded up so that the stored box contains the builder's box; an
+// unbounded axis is (0, +inf); ref[k] as above; unused children: half-extent -inf + kEmptyRef.
 struct alignas(16) WideNode {
   float box[4][6];
   int ref[4];

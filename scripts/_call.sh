@@ -1,5 +1,9 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "adaptive" > gpurun_out/r02c_pytest_adaptive.log 2>&1; tail -5 gpurun_out/r02c_pytest_adaptive.log
-(echo "== k_render_adaptive"; timeout 200 python scripts/gpu_adaptive.py 0 0 C2 C3 C5 C1; echo "== pixel stream (RT_B200_NO_ADAPTIVE_POOL=1)"; RT_B200_NO_ADAPTIVE_POOL=1 timeout 200 python scripts/gpu_adaptive.py 0 0 C2 C3 C5 C1) > gpurun_out/r02c_adaptive_ab.log 2>&1
-cat gpurun_out/r02c_adaptive_ab.log
+(timeout 300 python scripts/gpu_sah_vs_reference.py C3:1920:64 C4:3840:8 C1:400:16) > gpurun_out/r02c_sah_vs_ref.log 2>&1
+cat gpurun_out/r02c_sah_vs_ref.log
+timeout 600 python scripts/gpu_ab.py C3:64,C4:8,C1:16 old base > gpurun_out/r02c_node_ch_ab.log 2>&1
+cat gpurun_out/r02c_node_ch_ab.log
+timeout 600 python scripts/gpu_ab.py C4:8,C3:64 old base -- integrator=wavefront 2>&1
+timeout 600 python scripts/gpu_ab.py C4:16:1920,C3:64 old base -- aTolerance=0.05 2>&1
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
