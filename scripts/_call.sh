@@ -1,9 +1,12 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-(timeout 300 python scripts/gpu_sah_vs_reference.py C3:1920:64 C4:3840:8 C1:400:16) > gpurun_out/r02c_sah_vs_ref.log 2>&1
-cat gpurun_out/r02c_sah_vs_ref.log
-timeout 600 python scripts/gpu_ab.py C3:64,C4:8,C1:16 old base > gpurun_out/r02c_node_ch_ab.log 2>&1
-cat gpurun_out/r02c_node_ch_ab.log
-timeout 600 python scripts/gpu_ab.py C4:8,C3:64 old base -- integrator=wavefront 2>&1
-timeout 600 python scripts/gpu_ab.py C4:16:1920,C3:64 old base -- aTolerance=0.05 2>&1
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+(for q in 0 1; do
+  if [ $q = 1 ]; then export RT_B200_NO_QNODES=1; echo "== FP32 wide nodes (RT_B200_NO_QNODES=1)"; else echo "== quantised nodes"; fi
+  timeout 120 python scripts/prof_render.py C4 8 3
+  timeout 120 python scripts/prof_render.py C4 8 3 integrator=wavefront
+  timeout 120 python scripts/prof_render.py C4 8 3 aTolerance=0.05
+done) > gpurun_out/r02c_qnodes_ab.log 2>&1
+unset RT_B200_NO_QNODES
+cat gpurun_out/r02c_qnodes_ab.log
+timeout 300 python scripts/gpu_sah_vs_reference.py C4:3840:8 C4:960:32 2>&1 | tail -3
+timeout 900 python -m pytest tests -x -q -m gpu -k "rain or deep or trav or C4 or degenerate or primary" 2>&1 | tail -3
