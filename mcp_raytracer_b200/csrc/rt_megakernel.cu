@@ -1800,7 +1800,7 @@ constexpr int kTravNodesAdaptive = 16384; // deep trees keep k_render_stream_tra
 int render_adaptive_blocks(const DevScene& S, const RenderParams& R, int sms, int* warps) {
   static const bool off = getenv("RT_B200_NO_ADAPTIVE_POOL") != nullptr; // development switch
   if (off || !S.cam.adaptive || S.cam.mode != 0 || R.moments || S.cam.shadow_rays || R.pixstate || R.pass_cap > 0) return 0;
-  if (S.cam.a_batch < 1 || S.cam.a_batch * 32 > kAdMaxRecords) return 0;
+  if (S.cam.samples < 1 || S.cam.a_batch < 1 || S.cam.a_batch * 32 > kAdMaxRecords) return 0;
   if (S.bvh_kind == BVH_SAH && S.n_nodes >= kTravNodesAdaptive) return 0;
   int per_sm = 0;
   cudaError_t e;
