@@ -887,6 +887,9 @@ RT_DEV float cosine_pdf_value(V3 w_unit, V3 dir) { // pdf.ts:43-46
 
 // Light pdfs — quad.ts:123-158, sphere.ts:106-147.  A pdf evaluation is one single-primitive
 // hit test, never a traced ray.
+// The light records are read with 128-bit loads (DevLight is 16-byte aligned, p0..p3 at offset 0, q/u/v at 64): through a
+// `const DevLight&` the compiler read p0..p3 and q, u, v as 25 scalar LDG per diffuse bounce.
+RT_DEV const F4* light_f4(const DevLight& L) { return reinterpret_cast<const F4*>(&L); }
 template <class Scene>
 RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 dir) {
   Ray r{origin, dir};
@@ -895,16 +898,19 @@ RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 di
   if (L.type == OBJ_QUAD) {
     // (the axis-aligned specialisation of the LIST loops was measured here too: 16% slower on Cornell,
     //  it needs 1/d per axis for a single test)
-    int res = planar_test(L.p0, L.p1, L.p2, L.p3, true, r, pre, CUDART_INF_F, t);
+    const F4* lp = light_f4(L);
+    const F4 p0 = ldg4(lp);
+    int res = planar_test(p0, ldg4(lp + 1), ldg4(lp + 2), ldg4(lp + 3), true, r, pre, CUDART_INF_F, t);
     if (res == 2) res = exact_closer(S.exact, L.slot, -1, CUDART_INF_F, r, t) ? 1 : 0;
     float d2 = t * t * pre.a; // |rec.p - origin|^2
-    float cosine = fabsf(dot3(dir, xyz(L.p0)));
+    float cosine = fabsf(dot3(dir, xyz(p0)));
     return res == 1 ? d2 / (L.area * cosine) : 0.f;
   }
-  int res = sphere_test(L.p0, r, pre, CUDART_INF_F, t);
+  const F4 s0 = ldg4(light_f4(L));
+  int res = sphere_test(s0, r, pre, CUDART_INF_F, t);
   if (res == 2) res = exact_closer(S.exact, L.slot, -1, CUDART_INF_F, r, t) ? 1 : 0;
   if (res != 1) return 0.f;
-  V3 oc = xyz(L.p0) - origin;
+  V3 oc = xyz(s0) - origin;
   float d2 = dot3(oc, oc), r2 = L.radius * L.radius;
   if (d2 <= r2) return 0.07957747155f; // 1/(4 pi)
   float cos_theta = sqrtf(1.f - r2 / d2);
@@ -912,10 +918,12 @@ RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 di
 }
 RT_DEV V3 light_random_vec(const DevLight& L, V3 origin, float r1, float r2) {
   if (L.type == OBJ_QUAD) { // quad.ts:148-158 (alpha = r1, beta = r2)
-    V3 rp = fma3(r2, ld3(L.v), fma3(r1, ld3(L.u), ld3(L.q)));
+    const F4 a = ldg4(light_f4(L) + 4), b = ldg4(light_f4(L) + 5); // q.xyz u.x | u.yz v.xy
+    const float vz = L.v[2];
+    V3 rp = fma3(r2, mk3(b.z, b.w, vz), fma3(r1, mk3(a.w, b.x, b.y), mk3(a.x, a.y, a.z)));
     return normalize3(rp - origin);
   }
-  V3 oc = xyz(L.p0) - origin; // sphere.ts:140-147, vec3.ts:345-351
+  V3 oc = xyz(ldg4(light_f4(L))) - origin; // sphere.ts:140-147, vec3.ts:345-351
   float d2 = dot3(oc, oc);
   Onb b = make_onb(oc);
   float z = 1.f + r2 * (sqrtf(1.f - L.radius * L.radius / d2) - 1.f);

@@ -19,6 +19,7 @@
 //   lights  [n_lights] DevLight
 // Slots are primitives in BVH-leaf order, so a leaf is a contiguous slot range.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __CUDACC__
@@ -84,6 +85,7 @@ struct alignas(16) DevLight { // light = object with light:true that is a Sphere
   int slot;
   int pad;
 };
+static_assert(sizeof(DevLight) == 128 && offsetof(DevLight, q) == 64, "light_f4 (rt_device.cuh) reads DevLight as eight float4");
 
 struct DevCamera {
   float center[3], p00[3], du[3], dv[3], ddu[3], ddv[3];

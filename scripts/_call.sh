@@ -1,10 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-N=$1; WL=$2
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 5 --warmup 3 --workload $WL > gpurun_out/r02d_scale_n$N.jsonl 2> gpurun_out/r02d_scale_n$N.err
-python - <<PY
-import json
-for l in open("gpurun_out/r02d_scale_n$N.jsonl"):
-    j=json.loads(l); print(j["config"]["workload"][:24], j["n_gpus"], round(j["value"]), round(j["ms_per_step"],2), round(j["e2e"]["value"]), j["rank_ms"]["min"], j["rank_ms"]["max"], j["fb_sha1"][:12])
-PY
-tail -2 gpurun_out/r02d_scale_n$N.err
+timeout 600 python scripts/gpu_ab.py C2:256,C5:64 base lightvec lightvec2 base > gpurun_out/r02c_light_loads_ab.log 2>&1
+cat gpurun_out/r02c_light_loads_ab.log
