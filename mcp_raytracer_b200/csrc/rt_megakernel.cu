@@ -1025,7 +1025,21 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
     Rng g;
 
     for (;;) {
-      // ---- warp-level queue: lanes without a path take the next (pixel, sample) pairs in lane order ----
+      // ---- shading phase, part 1: finish the bounce of lanes whose ray is done ----
+      if (st == ST_HIT) {
+        const bool done = path_post<BVH_SAH>(S, nullptr, mw, ps, g, tv.tbest, tv.sbest);
+        st = done ? ST_NONE : ST_BEGIN;
+        if (done) {
+          acc_add(acc, lp, ps.radiance);
+          ++st_paths;
+          st_bounces += (unsigned)ps.bounces;
+          st_bmin = min(st_bmin, ps.bounces);
+          st_bmax = max(st_bmax, ps.bounces);
+        }
+      }
+      // ---- warp-level queue: lanes without a path take the next (pixel, sample) pairs in lane order.  AFTER the shading above:
+      //      a lane whose path just ended (a third of the shaded lanes on the 100 k-sphere scene) starts its next path in this
+      //      very round; with the queue at the top of the loop it sat out the whole traversal phase that follows ----
       const bool want = st == ST_NONE && !retired;
       const unsigned m = __ballot_sync(0xffffffffu, want);
       if (want) {
@@ -1042,18 +1056,7 @@ __global__ void __launch_bounds__(RT_TRAV_THREADS, RT_TRAV_BLOCKS) k_render_trav
       next += __popc(m);
       if (__all_sync(0xffffffffu, st == ST_NONE && retired)) break;
 
-      // ---- shading phase: finish the bounce of lanes whose ray is done, start the next bounce ----
-      if (st == ST_HIT) {
-        const bool done = path_post<BVH_SAH>(S, nullptr, mw, ps, g, tv.tbest, tv.sbest);
-        st = done ? ST_NONE : ST_BEGIN;
-        if (done) {
-          acc_add(acc, lp, ps.radiance);
-          ++st_paths;
-          st_bounces += (unsigned)ps.bounces;
-          st_bmin = min(st_bmin, ps.bounces);
-          st_bmax = max(st_bmax, ps.bounces);
-        }
-      }
+      // ---- shading phase, part 2: start the next bounce / the new path ----
       if (st == ST_BEGIN) {
         const uint32_t pixel = (uint32_t)pi_y * (uint32_t)cam.width + (uint32_t)pi_x;
         if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
