@@ -1874,6 +1874,7 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
   if (R.x1 <= R.x0 || R.y1 <= R.y0) return cudaSuccess;
   const long long tiles = (long long)R.tiles_x * R.tiles_y;
   constexpr int kTravNodes = 16384; // tree size from which resumable traversal beats the whole-query walk (see case BVH_SAH below)
+  constexpr int kTravNodesFixed = 6144; // ... for fixed-spp renders (k_render_pool<SAH> vs k_render_trav)
   if (render_needs_full(S, R)) {
     static const bool no_stream_trav = getenv("RT_B200_NO_STREAM_TRAV") != nullptr; // development switch
     if (S.cam.shadow_rays) { // whole-query walks for every tree size: the shadow ray is traced inside the shading step
@@ -1941,7 +1942,9 @@ cudaError_t launch_render_mega(const DevScene& S, const RenderParams& R, int sms
         return launch_persistent(k_render_sorted<BVH_SAH>, S, R, work, sms, st);
       }
       static const bool trav_always = getenv("RT_B200_TRAV_ALWAYS") != nullptr;
-      if (!trav_always && (no_trav || S.n_nodes < kTravNodes)) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
+      // fixed spp: crossover re-measured after the pair queue moved behind the shading (scripts/gpu_trav_threshold.py, rain scenes
+      // at 8 spp, pool / trav ms): 2730 node slots 7.08 / 7.85, 7956: 10.61 / 10.06, 15944: 16.08 / 12.32 (profiles/r02c_trav_threshold.log)
+      if (!trav_always && (no_trav || S.n_nodes < kTravNodesFixed)) return launch_persistent(k_render_pool<BVH_SAH, true>, S, R, work, sms, st);
       // (Measured and removed, round 2: TWO paths per lane — the active one in registers, the other parked in shared memory,
       //  swapped in when the active ray finishes so the lane keeps traversing; bit-identical image, 100 k spheres at 32 spp
       //  390 -> 417-436 ms over every min-lanes / burst setting: the swaps, the second service pass and the second traversal

@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 600 python scripts/gpu_ab.py C4:8,C4:16:1920 old base > gpurun_out/r02c_trav_fetch_after_shade.log 2>&1
-cat gpurun_out/r02c_trav_fetch_after_shade.log
-for m in 4 8 12 16; do echo "trav_min $m"; RT_B200_TRAV_MIN=$m timeout 100 python scripts/prof_render.py C4 8 2; done 2>&1 | tee -a gpurun_out/r02c_trav_fetch_after_shade.log
+(echo "== k_render_pool<SAH> (RT_B200_NO_TRAV=1)"; RT_B200_NO_TRAV=1 timeout 200 python scripts/gpu_trav_threshold.py 500 1000 2000 4000 8000 16000
+echo "== k_render_trav (RT_B200_TRAV_ALWAYS=1)"; RT_B200_TRAV_ALWAYS=1 timeout 200 python scripts/gpu_trav_threshold.py 500 1000 2000 4000 8000 16000
+echo "== C3 weekend-final @64"; timeout 100 python scripts/prof_render.py C3 64 3; RT_B200_TRAV_ALWAYS=1 timeout 100 python scripts/prof_render.py C3 64 3) > gpurun_out/r02c_trav_threshold.log 2>&1
+cat gpurun_out/r02c_trav_threshold.log
