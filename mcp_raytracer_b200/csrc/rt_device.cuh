@@ -614,7 +614,11 @@ struct BoxPre {
 };
 RT_DEV BoxPre box_precompute(const Ray& r) {
   BoxPre b;
+#ifdef RT_FAST_RCP // like precompute(): MUFU reciprocals, the slab tests pad the exit distance by 4 ulp
+  b.idir = V3{rcp_approx(r.d.x), rcp_approx(r.d.y), rcp_approx(r.d.z)};
+#else
   b.idir = V3{1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z};
+#endif
   b.oid = r.o * b.idir;
   return b;
 }
