@@ -521,10 +521,8 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
 // loop starts relative to the 128-byte instruction lines: an unrelated change that moved the tree walk of k_render_pool<SAH> by ONE
 // instruction cost weekend-final 5.8 % (36.1 -> 38.2 ms at 64 spp, same loop body; profiles/r02c_c3_regression.log).  CUDA C++ has
 // no alignment control for code, so the kernels can be shifted by N one-instruction no-ops executed once at kernel entry
-// (RT_PAD_LIST / RT_PAD_SAH, swept in profiles/r02c_code_pad_sweep.log).
-#ifndef RT_PAD_LIST
-#define RT_PAD_LIST 0
-#endif
+// (RT_PAD_SAH, swept in profiles/r02c_code_pad_sweep.log; k_render_pool<LIST>, k_render_trav, k_render_sorted and k_render_adaptive
+// were swept too and do not care: profiles/r02c_code_pad_sweep2.log).
 #ifndef RT_PAD_SAH
 #define RT_PAD_SAH 3 // weekend-final at 64 spp, pads 0..7: 38.1 38.4 38.0 36.9 37.2 37.3 37.8 38.2 ms; the LIST kernel does not care (26.44-26.54)
 #endif
@@ -536,7 +534,7 @@ RT_DEV void code_pad() {
 template <int KIND, bool POOL>
 __global__ void __launch_bounds__(KIND == BVH_LIST ? RT_LIST_THREADS : 256, KIND == BVH_LIST ? RT_LIST_BLOCKS : RT_MIN_BLOCKS)
 k_render_pool(const DevScene S, const RenderParams R) {
-  code_pad<KIND == BVH_LIST ? RT_PAD_LIST : (KIND == BVH_SAH ? RT_PAD_SAH : 0)>();
+  code_pad<KIND == BVH_SAH ? RT_PAD_SAH : 0>();
   __shared__ ListSmemData sm_data;
   __shared__ unsigned int s_acc[POOL ? (KIND == BVH_LIST ? RT_LIST_THREADS : 256) / 32 : 1][32 * 9];
   const ListSmem sm = stage_list<KIND>(S, sm_data);
