@@ -894,7 +894,13 @@ RT_DEV float cosine_pdf_value(V3 w_unit, V3 dir) { // pdf.ts:43-46
 // The light records are read with 128-bit loads (DevLight is 16-byte aligned, p0..p3 at offset 0, q/u/v at 64): through a
 // `const DevLight&` the compiler read p0..p3 and q, u, v as 25 scalar LDG per diffuse bounce.
 RT_DEV const F4* light_f4(const DevLight& L) { return reinterpret_cast<const F4*>(&L); }
-template <class Scene>
+// LV = false keeps the plain member reads: k_render_pool<LIST, false> — the bench kernel, at its 80-register cap — loses 1.9 %
+// to the four consecutive registers a vector load needs (Cornell 512 spp: 53.22 vs 54.24 ms, profiles/r02c_list_kernel_layout.log),
+// every other kernel gains (pair-queue LIST kernel 26.82 -> 26.48 ms at 256 spp, layered/mixed 72.4 -> 70.3 ms).
+template <bool LV>
+RT_DEV F4 light_ld4(const F4* p) { return LV ? ldg4(p) : *p; }
+#define RT_LIGHT_LD4(p) light_ld4<LV>(p)
+template <bool LV = true, class Scene>
 RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 dir) {
   Ray r{origin, dir};
   float t;
@@ -903,14 +909,14 @@ RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 di
     // (the axis-aligned specialisation of the LIST loops was measured here too: 16% slower on Cornell,
     //  it needs 1/d per axis for a single test)
     const F4* lp = light_f4(L);
-    const F4 p0 = ldg4(lp);
-    int res = planar_test(p0, ldg4(lp + 1), ldg4(lp + 2), ldg4(lp + 3), true, r, pre, CUDART_INF_F, t);
+    const F4 p0 = RT_LIGHT_LD4(lp);
+    int res = planar_test(p0, RT_LIGHT_LD4(lp + 1), RT_LIGHT_LD4(lp + 2), RT_LIGHT_LD4(lp + 3), true, r, pre, CUDART_INF_F, t);
     if (res == 2) res = exact_closer(S.exact, L.slot, -1, CUDART_INF_F, r, t) ? 1 : 0;
     float d2 = t * t * pre.a; // |rec.p - origin|^2
     float cosine = fabsf(dot3(dir, xyz(p0)));
     return res == 1 ? d2 / (L.area * cosine) : 0.f;
   }
-  const F4 s0 = ldg4(light_f4(L));
+  const F4 s0 = RT_LIGHT_LD4(light_f4(L));
   int res = sphere_test(s0, r, pre, CUDART_INF_F, t);
   if (res == 2) res = exact_closer(S.exact, L.slot, -1, CUDART_INF_F, r, t) ? 1 : 0;
   if (res != 1) return 0.f;
@@ -920,9 +926,10 @@ RT_DEV float light_pdf_value(const Scene& S, const DevLight& L, V3 origin, V3 di
   float cos_theta = sqrtf(1.f - r2 / d2);
   return 1.f / (6.28318530718f * (1.f - cos_theta));
 }
+template <bool LV = true>
 RT_DEV V3 light_random_vec(const DevLight& L, V3 origin, float r1, float r2) {
   if (L.type == OBJ_QUAD) { // quad.ts:148-158 (alpha = r1, beta = r2)
-    const F4 a = ldg4(light_f4(L) + 4), b = ldg4(light_f4(L) + 5); // q.xyz u.x | u.yz v.xy
+    const F4 a = RT_LIGHT_LD4(light_f4(L) + 4), b = RT_LIGHT_LD4(light_f4(L) + 5); // q.xyz u.x | u.yz v.xy
     const float vz = L.v[2];
     V3 rp = fma3(r2, mk3(b.z, b.w, vz), fma3(r1, mk3(a.w, b.x, b.y), mk3(a.x, a.y, a.z)));
     return normalize3(rp - origin);
@@ -955,7 +962,7 @@ RT_DEV MixW make_mixw(const Scene& S) {
 // The diffuse branch of rayColor, camera.ts:285-308 with the mixture pdf of pdf.ts:57-99, at hit point p with unit
 // normal n: `u_sel` picks the component (cosine | light k), (r1, r2) feed whichever generator was picked.
 // Out: the direction, cosv = the scatter pdf's value for it (pdf.ts:43-46), pdf_value = the mixture's.
-template <class Scene>
+template <bool LV = true, class Scene>
 RT_DEV void diffuse_bounce(const Scene& S, const MixW& mw, V3 p, V3 n, float u_sel, float r1, float r2, V3& dir, float& cosv,
                            float& pdf_value) {
   const Onb onb = make_onb<true>(n);
@@ -968,13 +975,13 @@ RT_DEV void diffuse_bounce(const Scene& S, const MixW& mw, V3 p, V3 n, float u_s
       partial += mw.wl;
       if (rnd < partial) { chosen = k; break; }
     }
-    V3 ldir = light_random_vec(S.lights[chosen], p, r1, r2);
+    V3 ldir = light_random_vec<LV>(S.lights[chosen], p, r1, r2);
     dir = sel3(rnd < 0.5f, dir, ldir);
   }
   const float cz = dot3(dir, onb.w); // all three generators return unit vectors
   cosv = cz <= 0.f ? 0.f : cz * 0.31830988618f;
   float sum = 0.5f * cosv;
-  for (int k = 0; k < mw.nl; ++k) sum = fmaf(mw.wl, light_pdf_value(S, S.lights[k], p, dir), sum);
+  for (int k = 0; k < mw.nl; ++k) sum = fmaf(mw.wl, light_pdf_value<LV>(S, S.lights[k], p, dir), sum);
   pdf_value = sum * mw.inv_total_w;
 }
 

@@ -140,7 +140,7 @@ RT_DEV bool path_pre(const DevCamera& cam, PathState& ps, Rng& g) {
 // rayColor, part 2 (camera.ts:249-319) given the closest hit (slot < 0: miss).  True = the path ended
 // (its radiance is complete); otherwise ps.ray / ps.tp / ps.bounces describe the next call.
 #ifndef RT_SINGLE_EXIT
-template <int KIND>
+template <int KIND, bool LV = true> // LV: light records by 128-bit loads (light_ld4, rt_device.cuh)
 RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t, int slot) {
   const DevCamera& cam = S.cam;
   if (slot < 0) { // camera.ts:252-258
@@ -176,7 +176,7 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
   const float u_sel = g.next(), r1 = g.next(), r2 = g.next();
   V3 dir;
   float cosv, pdf_value;
-  diffuse_bounce(S, mw, sf.p, sf.n, u_sel, r1, r2, dir, cosv, pdf_value);
+  diffuse_bounce<LV>(S, mw, sf.p, sf.n, u_sel, r1, r2, dir, cosv, pdf_value);
   if (!(pdf_value > 0.0001f)) return true; // camera.ts:298-301 (NaN also ends the path)
   ps.tp = ps.tp * (sc.attenuation * (cosv * rcp_approx(pdf_value)));
   ps.ray = Ray{sf.p, dir};
@@ -185,7 +185,7 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
 #else
 // Single-exit form: every branch rejoins before the next one starts, so the diffuse and the specular update are
 // laid out once each and the warp reconverges between the stages (miss | emission + dispatch | scatter | update).
-template <int KIND>
+template <int KIND, bool LV = true> // LV: light records by 128-bit loads (light_ld4, rt_device.cuh)
 RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, PathState& ps, Rng& g, float t, int slot) {
   const DevCamera& cam = S.cam;
   int kind = SCATTER_NONE;
@@ -218,7 +218,7 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
   if (kind == SCATTER_DIFFUSE) { // camera.ts:285-315 with the mixture pdf of pdf.ts:57-99
     const float u_sel = g.next(), r1 = g.next(), r2 = g.next();
     float cosv, pdf_value;
-    diffuse_bounce(S, mw, sf.p, sf.n, u_sel, r1, r2, sdir, cosv, pdf_value);
+    diffuse_bounce<LV>(S, mw, sf.p, sf.n, u_sel, r1, r2, sdir, cosv, pdf_value);
     att = att * (cosv * rcp_approx(pdf_value));
     if (!(pdf_value > 0.0001f)) kind = SCATTER_NONE; // camera.ts:298-301 (NaN also ends the path)
   }
@@ -230,14 +230,14 @@ RT_DEV bool path_post(const DevScene& S, const ListSmem* sm, const MixW& mw, Pat
 #endif
 
 // One whole rayColor call on the path's current ray.
-template <int KIND, bool LEAF_LOOP = true>
+template <int KIND, bool LEAF_LOOP = true, bool LV = true>
 RT_DEV bool path_step(const DevScene& S, const SmemList& L, const ListSmem& sm, const MixW& mw, PathState& ps, Rng& g,
                       WorkCount& wc) {
   if (path_pre(S.cam, ps, g)) return true;
   float t;
   int slot;
   closest_hit<KIND, LEAF_LOOP>(S, L, ps.ray, t, slot, wc); // world.hit(r, (0.001, inf)) — camera.ts:249
-  return path_post<KIND>(S, &sm, mw, ps, g, t, slot);
+  return path_post<KIND, LV>(S, &sm, mw, ps, g, t, slot);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -523,6 +523,9 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
 // no alignment control for code, so the kernels can be shifted by N one-instruction no-ops executed once at kernel entry
 // (RT_PAD_SAH, swept in profiles/r02c_code_pad_sweep.log; k_render_pool<LIST>, k_render_trav, k_render_sorted and k_render_adaptive
 // were swept too and do not care: profiles/r02c_code_pad_sweep2.log).
+#ifndef RT_PAD_LIST
+#define RT_PAD_LIST 0
+#endif
 #ifndef RT_PAD_SAH
 #define RT_PAD_SAH 3 // weekend-final at 64 spp, pads 0..7: 38.1 38.4 38.0 36.9 37.2 37.3 37.8 38.2 ms; the LIST kernel does not care (26.44-26.54)
 #endif
@@ -534,7 +537,7 @@ RT_DEV void code_pad() {
 template <int KIND, bool POOL>
 __global__ void __launch_bounds__(KIND == BVH_LIST ? RT_LIST_THREADS : 256, KIND == BVH_LIST ? RT_LIST_BLOCKS : RT_MIN_BLOCKS)
 k_render_pool(const DevScene S, const RenderParams R) {
-  code_pad<KIND == BVH_SAH ? RT_PAD_SAH : 0>();
+  code_pad<KIND == BVH_SAH ? RT_PAD_SAH : (KIND == BVH_LIST && !POOL ? RT_PAD_LIST : 0)>();
   __shared__ ListSmemData sm_data;
   __shared__ unsigned int s_acc[POOL ? (KIND == BVH_LIST ? RT_LIST_THREADS : 256) / 32 : 1][32 * 9];
   const ListSmem sm = stage_list<KIND>(S, sm_data);
@@ -595,7 +598,7 @@ k_render_pool(const DevScene S, const RenderParams R) {
         if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
         g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
-        ended = path_step<KIND>(S, L, sm, mw, ps, g, wc);
+        ended = path_step<KIND, true, !(KIND == BVH_LIST && !POOL)>(S, L, sm, mw, ps, g, wc); // (LV: see light_ld4)
       }
 #ifndef RT_NO_RECONVERGE
       // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
@@ -1696,7 +1699,7 @@ __global__ void __launch_bounds__(ad_threads(KIND), ad_blocks(KIND)) k_render_ad
           if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
           gen.begin(pixel, (uint32_t)(s_done + s_in), (uint32_t)ps.bounces, S.seed_lo, S.seed_hi);
           if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, gen, true);
-          ended = path_step<KIND, false>(S, L, sm, mw, ps, gen, wc);
+          ended = path_step<KIND, false, KIND != BVH_LIST>(S, L, sm, mw, ps, gen, wc); // (LV: Cornell defaults 60.2 -> 58.2 ms at 512 spp without the vector loads)
         }
         __syncwarp(); // one copy of the end-of-sample code (see k_render_pool)
         if (ended) {
