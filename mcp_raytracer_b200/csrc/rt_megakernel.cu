@@ -527,7 +527,7 @@ RT_DEV unsigned item_epilogue(const RenderParams& R, const DevCamera& cam, const
 #define RT_PAD_LIST 0
 #endif
 #ifndef RT_PAD_SAH
-#define RT_PAD_SAH 3 // weekend-final at 64 spp, pads 0..7: 38.1 38.4 38.0 36.9 37.2 37.3 37.8 38.2 ms; the LIST kernel does not care (26.44-26.54)
+#define RT_PAD_SAH 3 // weekend-final at 64 spp, pads 0..7 (with the vector light loads): 38.1 38.4 38.0 36.9 37.2 37.3 37.8 38.2 ms; with member reads 36.0 (pad 0), 35.9 (pad 3); the LIST kernel does not care (26.44-26.54)
 #endif
 template <int N>
 RT_DEV void code_pad() {
@@ -598,7 +598,9 @@ k_render_pool(const DevScene S, const RenderParams R) {
         if (fresh) { ps.tp = mk3(1, 1, 1); ps.radiance = mk3(0, 0, 0); ps.bounces = 0; }
         g.begin(pixel, (uint32_t)sample, (uint32_t)ps.bounces, S.seed_lo, S.seed_hi); // one Philox block per bounce
         if (fresh) ps.ray = camera_ray(cam, pi_x, pi_y, g, true);
-        ended = path_step<KIND, true, !(KIND == BVH_LIST && !POOL)>(S, L, sm, mw, ps, g, wc); // (LV: see light_ld4)
+        // LV (light_ld4): member reads for the lane-keeps-pixel LIST kernel and for the tree walk — the vector loads cost them
+        // 1.9 % (Cornell) and 3 % (weekend-final, which has no light at all: register allocation and code placement of the walk)
+        ended = path_step<KIND, true, (KIND == BVH_LIST && POOL) || KIND == BVH_REFERENCE>(S, L, sm, mw, ps, g, wc);
       }
 #ifndef RT_NO_RECONVERGE
       // every way a path can end (miss, light, absorbed, roulette, depth, pdf 0) meets here: ONE copy of the end-of-path code
