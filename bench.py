@@ -519,6 +519,21 @@ def bench_workload(args, workload, rank, world, local_rank, emit, env):
                 roof["achieved"], roof["frac"], roof["flops_per_path"] = ex, ex / peak, ray_flops + shade
                 roof["flops_model"] = "SURVEY.md §8d constants on the events the device executes on its own 4-wide SAH tree; reference-tree figure under reference_tree"
 
+    # The same workload with the reference's DEFAULT render options (adaptive sampling on: aTolerance 0.05, aBatch 10 —
+    # src/camera.ts:73-83; the headline config turns it off).  One GPU only, outside every timed region, never part of `value`.
+    ref_defaults = None
+    if world == 1:
+        try:
+            with createCameraFromSceneData(sd, {**ropts, "aTolerance": 0.05, "aBatch": 10}) as ac:
+                abuf = np.zeros(W * H * 3, np.uint8)
+                ast = min((ac.render(abuf) for _ in range(2)), key=lambda s_: s_.deviceMs)
+            ref_defaults = {"aTolerance": 0.05, "aBatch": 10, "value": ast.samples["total"] / ast.deviceMs / 1e3, "unit": "Mpaths/s",
+                            "grays_per_s": ast.rays / ast.deviceMs / 1e6, "ms": ast.deviceMs, "samples_taken": int(ast.samples["total"]),
+                            "samples_at_fixed_spp": paths_per_step,
+                            "note": "device time of one render (best of 2), scene resident; not the headline configuration"}
+        except Exception as e:  # never lets the optional figure break the bench line
+            ref_defaults = {"error": str(e)[:200]}
+
     line = {
         "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -539,6 +554,7 @@ def bench_workload(args, workload, rank, world, local_rank, emit, env):
                 "includes": "SceneData flatten + BVH build + H2D + render + gather + D2H of the RGB8 framebuffer and stats"},
         "gpu_launches": kernel_launches_per_step * args.steps * world,
         "roofline": roof, "cpu_baseline": cpu,
+        "reference_defaults_adaptive": ref_defaults,
     }
     emit(line)
     cam.close()

@@ -548,6 +548,23 @@ def test_sorted_integrator_equals_megakernel(gpu, name, width, spp, bvh):
     assert np.all(buf[~inside] == 77) and np.array_equal(buf[inside], a["rgb8"][inside])
 
 
+@pytest.mark.parametrize("name,opts", [
+    ("C1-spheres", {"width": 400, "samples": 16, "depth": 10}),          # whole-query walk (k_render_pool<SAH>)
+    ("C3-weekend", {"width": 320, "samples": 24}),                        # ... with the ground sphere in the always-tested prefix
+    ("C4-rain", {"width": 320, "samples": 6}),                            # 20 k spheres: resumable traversal (k_render_trav)
+])
+def test_sah_walk_gives_the_image_of_the_reference_topology_walk(gpu, name, opts):
+    """The 4-wide SAH nodes hold (centre, half-extent) boxes with the half-extents rounded up and are tested with a slab test of
+    their own; the reference-topology tree holds the true min / max boxes.  Both walks decide every hit with the same primitive
+    tests, so with the same seed they must give the same image — unless a box test drops a box the ray enters."""
+    sd = SCENES[name]()
+    opts = {"aTolerance": 0, "seed": 5, **opts}
+    a = gpu_render(sd, {**opts, "bvh": "sah"})
+    b = gpu_render(sd, {**opts, "bvh": "reference"})
+    assert (a["stats"].samples, a["stats"].rays, a["stats"].bounces) == (b["stats"].samples, b["stats"].rays, b["stats"].bounces)
+    assert np.array_equal(a["linear"], b["linear"]) and np.array_equal(a["rgb8"], b["rgb8"])
+
+
 def test_deep_tree_state_machine_kernel(gpu):
     """Big trees run k_render_trav (resumable traversal bursts interleaved with shading): same image as the
     wavefront integrator (its own extend kernel) and as the union of a 3-way partition; primary hits vs the oracle."""
