@@ -25,6 +25,11 @@
 // at a time and runs the reference's loop (src/camera.ts:400-423) in sample order, as the adaptive exit rule
 // requires; lanes pull the next pixel from their warp's stream when theirs stops.
 //
+// k_render_adaptive (plain adaptive renders — the reference's DEFAULT options — of every scene the whole-query kernels serve):
+// the exit rule needs a pixel's batch to be complete, not to have run on one lane.  A warp item is one batch of a group of
+// pixels; its (pixel, sample) pairs go through the pair queue of k_render_pool, every finished sample is a 16-byte record, and
+// one lane per pixel then adds the records in sample order and decides — bit for bit the sums and decisions of k_render_stream.
+//
 // All path state lives in registers; HBM sees the scene reads (L1/L2 resident), 24 B of atomics per
 // (pixel, chunk) when chunks > 1, and 3 bytes per pixel of output.
 #include <algorithm>
