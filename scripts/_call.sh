@@ -1,4 +1,3 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "reference_topology_walk or deep_tree" 2>&1 | tail -3
-timeout 200 python bench.py --steps 2 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; j=json.loads(sys.stdin.read()); print(j['value'], j['reference_defaults_adaptive'])"
+(for b in 3 4 5 6 8; do for m in 8 12; do echo -n "burst $b min $m: "; RT_B200_TRAV_BURST=$b RT_B200_TRAV_MIN=$m timeout 100 python scripts/prof_render.py C4 8 3; done; done) 2>&1 | tee gpurun_out/r02c_trav_burst_sweep.log
