@@ -191,6 +191,8 @@ struct alignas(8) PixState {
   unsigned int bounces;
   int done; // converged or all samples taken: later passes skip the pixel
 };
+static_assert(sizeof(PixState) == 40 && offsetof(PixState, samples) == 12 && offsetof(PixState, sum_ill) == 16 && offsetof(PixState, bounces) == 32,
+              "adstate_load / adstate_store (rt_megakernel.cu) move a PixState as five 64-bit words");
 // ---- wavefront integrator (rt_wavefront.cuh): path pool + queues in HBM ----
 struct U2 { uint32_t x, y; };
 enum : int { WF_TAGS = 3 };
