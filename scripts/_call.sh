@@ -1,5 +1,3 @@
-# last check of the committed tree: full GPU suite + smoke
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu > gpurun_out/r02h_pytest_gpu_full.log 2>&1; tail -3 gpurun_out/r02h_pytest_gpu_full.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 300 python scripts/gpu_ab.py C4:8,C3:64 base trial base trial 2>&1 | tee gpurun_out/r02c_trial_refill.log
