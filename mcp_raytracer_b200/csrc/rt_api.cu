@@ -691,7 +691,9 @@ static rt_status enqueue_render(rt_camera* c, RenderParams& P, rt_stats* stats_d
       static const int trav_env = getenv("RT_B200_TRAV_MIN") ? atoi(getenv("RT_B200_TRAV_MIN")) : -1; // development override
       static const int burst_env = getenv("RT_B200_TRAV_BURST") ? atoi(getenv("RT_B200_TRAV_BURST")) : -1; // development override
       // swept on the 100k-sphere scene with the 4-wide tree (8 spp, ms): burst 4: min 4/8/10/12/16/20 = 118/116/116/118/124/133;
-      // burst 6: 123/119/119/120/124/131; burst 2 and 8 are worse at every setting
+      // burst 6: 123/119/119/120/124/131; burst 2 and 8 are worse at every setting.  After the pair queue moved behind the shading
+      // (k_render_trav) and the sampler change: burst 3/4/5/6/8 at min 8: 86.8/86.9/87.8/90.7/93.4, at min 12: 86.6/86.4/87.1/89.9/92.3
+      // (profiles/r02c_trav_burst_sweep.log) — flat around the settings below
       P.trav_min_lanes = trav_env >= 0 ? trav_env : 8;
       P.trav_burst = burst_env >= 1 ? burst_env : 4;
     }
